@@ -1,0 +1,29 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "ref_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def default_costs(golden):
+    return golden["default_costs"]
+
+
+@pytest.fixture(scope="session")
+def user_costs(golden):
+    return golden["user_costs"]

@@ -1,0 +1,103 @@
+// rsd_ctx.cuh — the context object behind the opaque rsd_ctx handle (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <unistd.h>
+#include <new>
+
+#include "k_plan.cuh"
+
+int rsd_fail(int code, const char *fmt, ...);
+
+#define RSD_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                     \
+            return rsd_fail(e__ == cudaErrorMemoryAllocation ? RSD_ENOMEM : RSD_ECUDA, "%s: %s (%s:%d)", #call, \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                          \
+        }                                                                                           \
+    } while (0)
+
+#define RSD_OK_OR_RETURN(call)            \
+    do {                                  \
+        int rc__ = (call);                \
+        if (rc__ != 0) return rc__;       \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes + 256);
+            want = bytes + 256;
+            if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return rsd_fail(4 /*RSD_ENOMEM*/, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct SeqBufs { DevBuf words, start, len; void release() { words.release(); start.release(); len.release(); } };
+
+struct ModeInfo {
+    int mode;       // RSD_MODE_*
+    int k;          // scale_log2 (int modes)
+    IntCosts ic;
+    F64Costs fc;
+};
+
+struct rsd_ctx {
+    int device = 0;
+    bool inited = false;
+    pid_t pid = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false, timed = false;
+    int64_t launches = 0;
+
+    bool have_costs = false;
+    double ins = 0, del = 0, sub[15][15];
+    IntCosts *d_ic = nullptr;
+    F64Costs *d_fc = nullptr;
+
+    SeqBufs bufA, bufB, bufX, bufQ;
+    DevBuf out_f64, scratch, plan_pair_bin, plan_bins, plan_groups;
+    DevBuf mat_vals, mat_mask, mat_ab;
+    // script / patch
+    DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, p_out, p_len, p_err, misc;
+    // database shard
+    SeqBufs db;
+    int64_t db_n = 0, db_base = 0, db_nwords = 0, db_maxlen = 0;
+    int db_bits = 0;
+    uint32_t db_symmask = 0;
+    DevBuf db_dist, db_topi, db_tops, db_aux;
+
+    int ensure_device();
+    int classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, int force_mode, ModeInfo &mi) const;
+    int upload_costs(const ModeInfo &mi, cudaStream_t st);
+    int upload_seqs(SeqBufs &sb, const uint32_t *words, const int64_t *start, const int32_t *len, int64_t n,
+                    int64_t n_words, cudaStream_t st);
+    int make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin, double *d_out,
+                  cudaStream_t st, PlanView &pv);
+    int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
+                     const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
+                     int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
+    void free_all() {
+        bufA.release(); bufB.release(); bufX.release(); bufQ.release(); db.release();
+        DevBuf *all[] = {&out_f64, &scratch, &plan_pair_bin, &plan_bins, &plan_groups, &mat_vals, &mat_mask, &mat_ab,
+                         &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &p_out, &p_len, &p_err, &misc,
+                         &db_dist, &db_topi, &db_tops, &db_aux};
+        for (DevBuf *b : all) b->release();
+    }
+};

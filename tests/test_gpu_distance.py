@@ -1,0 +1,218 @@
+"""GPU parity: distances and matrices through the C ABI vs the oracle and the reference's golden
+vectors.  Bit-exact (==) everywhere: integer modes are exact by construction, fp64 mode follows
+the reference's operation order."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def R():
+    import __graft_entry__ as G
+    G.build()
+    import rna_sequence_diff_patch_b200 as R
+    assert R.load_library().rsd_device_count() > 0, "no CUDA device: GPU tests need the B200 box"
+    return R
+
+
+@pytest.fixture(scope="module")
+def eng(R):
+    return R.Engine(0)
+
+
+def rand_seqs(rng, n, lo, hi, alphabet):
+    al = np.array(list(alphabet))
+    lens = rng.integers(lo, hi + 1, size=n)
+    return ["".join(al[rng.integers(0, len(al), size=L)]) for L in lens]
+
+
+def oracle_batch(a, b, costs):
+    ac, ao = O.concat(a); bc, bo = O.concat(b)
+    return O.distance_batch(ac, ao, bc, bo, costs)
+
+
+def test_dropin_golden_matrices(R, golden):
+    sys.path.insert(0, os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    try:
+        import StringEditDistance as S
+        assert S.default_costs == golden["default_costs"] and S.user_costs == golden["user_costs"]
+        dp = S.wagnerFisher('AGRGA', 'AGGGAA', True)
+        assert str(dp) == golden["G1"]["dp_str"]
+        paths = S.create_paths(dp)
+        assert [S.generate_es(p, 'AGRGA', 'AGGGAA') for p in paths] == golden["G1"]["es"][:len(paths)]
+        n = 0
+        for c in [golden["G1"]] + golden["small"] + golden["medium"]:
+            dp = S.wagnerFisher(c["a"], c["b"], c["user"])
+            assert dp[len(dp) - 1][len(dp[0]) - 1].value == c["distance"]
+            if "dp_repr" in c:
+                assert [[repr(x.value) for x in row] for row in dp] == c["dp_repr"]
+                assert dp.mask.tolist() == c["mask"]
+            if "es" in c:
+                paths = S.create_paths(dp)
+                assert len(paths) == c["n_paths"]
+                es0 = S.generate_es(paths[0], c["a"], c["b"])
+                assert es0 == c["es"][0]
+                assert list(S.patching(es0, c["a"])) == c["patch0"]
+                rev = S.generate_rev_es(es0)
+                assert list(S.patching(rev, c["b"])) == c["rev_patch0"]
+            n += 1
+        assert n > 300
+        for c in golden["symbols"]:
+            if "error" in c:
+                with pytest.raises(KeyError):
+                    S.wagnerFisher(c["a"], c["b"])
+            else:
+                dp = S.wagnerFisher(c["a"], c["b"])
+                assert [[repr(x.value) for x in row] for row in dp] == c["dp_repr"]
+        for c in golden["empties"]:
+            dp = S.wagnerFisher(c["a"], c["b"])
+            assert [[repr(x.value) for x in row] for row in dp] == c["dp_repr"]
+    finally:
+        os.chdir(cwd)
+
+
+def test_xml_600_pairs_both_tables(R, eng, golden):
+    seqs = golden["xml_seqs"]
+    ii = [r[0] for r in golden["xml_all_pairs"]]; jj = [r[1] for r in golden["xml_all_pairs"]]
+    A = R.pack([seqs[i] for i in ii]); B = R.pack([seqs[j] for j in jj])
+    for col, costs in ((2, golden["default_costs"]), (3, golden["user_costs"])):
+        eng.set_costs(costs)
+        want = np.array([r[col] for r in golden["xml_all_pairs"]])
+        for force in (0, 2, 3):
+            got = eng.distance_batch(A, B, force_mode=force)
+            assert np.array_equal(got, want), (col, force)
+    assert eng.last_mode == 3
+
+
+def test_g6_fp64_fingerprints(R, eng, golden):
+    eng.set_costs(golden["default_costs"])
+    A = R.pack([c["a"] for c in golden["G6"]]); B = R.pack([c["b"] for c in golden["G6"]])
+    got = eng.distance_batch(A, B)
+    assert eng.last_mode == 3
+    assert got.tolist() == [c["distance"] for c in golden["G6"]]
+    assert got.tolist() == [66.74999999999994, 125.39999999999989, 191.40999999999983, 315.9600000000003,
+                            628.7499999999999]
+
+
+@pytest.mark.parametrize("table", ["user", "default"])
+def test_acgu_batch_all_modes_agree_with_oracle(R, eng, golden, table):
+    costs = golden[f"{table}_costs"]
+    eng.set_costs(costs)
+    rng = np.random.default_rng(11)
+    a = rand_seqs(rng, 3000, 100, 300, "AGCU"); b = rand_seqs(rng, 3000, 100, 300, "AGCU")
+    want = oracle_batch(a, b, costs)
+    A, B = R.pack(a), R.pack(b)
+    assert A.bits == 2
+    got = eng.distance_batch(A, B)
+    assert eng.last_mode == 1, "ACGU with integer costs must take the int16x2 DPX path"
+    assert np.array_equal(got, want)
+    for force in (2, 3):
+        assert np.array_equal(eng.distance_batch(A, B, force_mode=force), want), force
+    A4, B4 = A.repack(4), B.repack(4)
+    for force in (0, 2, 3):
+        assert np.array_equal(eng.distance_batch(A4, B4, force_mode=force), want), force
+
+
+def test_iupac_batch_fp64(R, eng, golden):
+    rng = np.random.default_rng(12)
+    a = rand_seqs(rng, 2000, 100, 300, R.SYMBOLS); b = rand_seqs(rng, 2000, 100, 300, R.SYMBOLS)
+    for costs in (golden["default_costs"], golden["user_costs"]):
+        eng.set_costs(costs)
+        got = eng.distance_batch(R.pack(a), R.pack(b))
+        assert eng.last_mode == 3
+        assert np.array_equal(got, oracle_batch(a, b, costs))
+
+
+def test_dyadic_subset_int32_scaled(R, eng, golden):
+    """{A,G,C,U,Y,R,W,S,K,M,N} under default costs: everything is a multiple of 0.25 -> int32 x4."""
+    rng = np.random.default_rng(13)
+    al = "AGCUYRWSKMN"
+    a = rand_seqs(rng, 1500, 20, 120, al); b = rand_seqs(rng, 1500, 20, 120, al)
+    eng.set_costs(golden["default_costs"])
+    got = eng.distance_batch(R.pack(a), R.pack(b))
+    assert eng.last_mode == 2
+    want = oracle_batch(a, b, golden["default_costs"])
+    assert np.array_equal(got, want)
+    assert np.array_equal(eng.distance_batch(R.pack(a), R.pack(b), force_mode=3), want)
+
+
+def test_edge_lengths_and_multipass(R, eng, golden):
+    """Empty and ragged inputs, strip boundaries (C = 32 / 16 columns per lane), > 32 strips."""
+    rng = np.random.default_rng(14)
+    lens = [0, 1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 95, 96, 97, 511, 512, 513, 1023, 1024, 1025, 1100, 2050]
+    al = np.array(list("AGCU"))
+    a, b = [], []
+    for la in lens:
+        for lb in (0, 1, 31, 32, 33, 64, 100, 513, 1024, 1025, 2049):
+            if la * lb > 1_300_000:
+                continue
+            a.append("".join(al[rng.integers(0, 4, size=la)])); b.append("".join(al[rng.integers(0, 4, size=lb)]))
+    for costs in (golden["user_costs"], golden["default_costs"]):
+        eng.set_costs(costs)
+        want = oracle_batch(a, b, costs)
+        A, B = R.pack(a), R.pack(b)
+        for force in (0, 2, 3):
+            got = eng.distance_batch(A, B, force_mode=force)
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, (force, [(len(a[k]), len(b[k]), got[k], want[k]) for k in bad[:5]])
+    # the same shapes over the full alphabet (fp64, 4-bit)
+    al15 = np.array(list(R.SYMBOLS))
+    a15 = ["".join(al15[rng.integers(0, 15, size=len(x))]) for x in a]
+    b15 = ["".join(al15[rng.integers(0, 15, size=len(x))]) for x in b]
+    eng.set_costs(golden["default_costs"])
+    got = eng.distance_batch(R.pack(a15), R.pack(b15))
+    assert np.array_equal(got, oracle_batch(a15, b15, golden["default_costs"]))
+
+
+def test_single_pair_and_tiny_batches(R, eng, golden):
+    eng.set_costs(golden["default_costs"])
+    for n in (1, 2, 3, 33):
+        a = ["ACGUACGUAC"] * n; b = ["ACGUUCGUA"] * n
+        got = eng.distance_batch(R.pack(a), R.pack(b))
+        assert got.tolist() == [O.distance(a[0], b[0], golden["default_costs"])] * n
+    assert eng.distance_batch(R.pack([]), R.pack([])).shape == (0,)
+
+
+def test_large_batch_property_identity_and_symmetry(R, eng, golden):
+    """BASELINE-size property checks that need no oracle: d(x,x) == 0; with ins == del and a
+    symmetric table d(a,b) == d(b,a); duplicating a batch duplicates its answers."""
+    eng.set_costs(golden["default_costs"])
+    rng = np.random.default_rng(15)
+    a = rand_seqs(rng, 60000, 100, 300, "AGCU"); b = rand_seqs(rng, 60000, 100, 300, "AGCU")
+    A, B = R.pack(a), R.pack(b)
+    d_ab = eng.distance_batch(A, B); d_ba = eng.distance_batch(B, A)
+    assert np.array_equal(d_ab, d_ba)
+    assert not eng.distance_batch(A, A).any()
+    sub = rng.choice(60000, size=400, replace=False)
+    want = oracle_batch([a[k] for k in sub], [b[k] for k in sub], golden["default_costs"])
+    assert np.array_equal(d_ab[sub], want)
+
+
+def test_wf_score_and_search_collection_g7(R, golden):
+    sys.path.insert(0, os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    try:
+        import IRMethods as IR
+
+        class Coll:
+            def __init__(self, docs): self.docs = docs
+            def find(self, flt): return iter(self.docs)
+        coll = Coll([{"sequence": s} for s in golden["xml_seqs"]])
+        for c in golden["G7"]:
+            scores = IR.search_collection(c["query"], 'tf', coll, IR.wf_score)
+            assert [list(x) for x in scores] == c["scores"]
+            assert [list(x) for x in IR.top_k(scores, 6)] == c["top6"]
+        for a, b, v in golden["wf_score_user"]:
+            assert IR.wf_score(a, b, True) == v
+    finally:
+        os.chdir(cwd)

@@ -16,6 +16,7 @@
 // Direction storage: dirs[pair][rb][col] is one u32 holding rows 16*rb .. 16*rb+15 of column col
 // (2 bits each, row r at bits 2*(r & 15)); col < n_pad = strips * C.  Codes: 0 INS, 1 DEL, 2 UPD.
 #pragma once
+#include <type_traits>
 #include "k_dist.cuh"
 
 struct ScriptView {
@@ -223,7 +224,8 @@ __global__ void k_traceback(const int32_t *__restrict__ a_len, const int32_t *__
 // compares the patched string with B.
 // ------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
-    const uint8_t *tmp; int64_t max_ops; const int32_t *n_ops;          // traced ops (end-aligned in slot of m+n)
+    const uint8_t *tmp; int64_t max_ops; const int32_t *n_ops;          // ops per pair slot
+    int end_aligned;                                                      // 1: ops end at slot offset m+n (traceback), 0: start at 0
     SeqView A, B, X; int bits;                                            // X == A for the round-trip check
     uint8_t *op; int32_t *oi; int32_t *oj;                                // optional packed script outputs (may be NULL)
     int64_t out_stride;                                                   // stride of op/oi/oj slots
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs fa, int64_t n_pai
     const int tid = threadIdx.x;
     const int m = fa.A.len[p], n = fa.B.len[p];
     const int k_ops = fa.n_ops[p];
-    const uint8_t *src = fa.tmp + p * fa.max_ops + ((int64_t)m + n - k_ops);
+    const uint8_t *src = fa.tmp + p * fa.max_ops + (fa.end_aligned ? ((int64_t)m + n - k_ops) : 0);
     const int64_t a0 = fa.A.start[p], b0 = fa.B.start[p];
     const bool do_patch = fa.patched != nullptr || fa.ok != nullptr || fa.err != nullptr;
     const int xlen = do_patch ? fa.X.len[p] : 0;

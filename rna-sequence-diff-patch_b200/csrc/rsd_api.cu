@@ -13,6 +13,7 @@
 #include "k_dist.cuh"
 #include "k_matrix.cuh"
 #include "k_ubench.cuh"
+#include "k_script.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -512,17 +513,6 @@ extern "C" int rsd_topk_merge(const int64_t *idx, const double *score, int n_sha
 }
 
 #include "rsd_stubs.cuh"
-extern "C" int rsd_script_batch(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t,
-                                const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t, int,
-                                int64_t, uint8_t *, int32_t *, int32_t *, int32_t *, double *, int *) { RSD_NOT_YET("rsd_script_batch"); }
-extern "C" int rsd_patch_batch(rsd_ctx *, const uint8_t *, const int32_t *, const int32_t *, const int32_t *, int64_t,
-                               const uint32_t *, const int64_t *, const int32_t *, int64_t,
-                               const uint32_t *, const int64_t *, const int32_t *, int64_t,
-                               const uint32_t *, const int64_t *, const int32_t *, int64_t,
-                               int64_t, int, int64_t, uint8_t *, int32_t *, int32_t *) { RSD_NOT_YET("rsd_patch_batch"); }
-extern "C" int rsd_script_patch_check_batch(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t,
-                                const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t, int,
-                                int64_t, uint8_t *, int32_t *, int32_t *, int32_t *, double *, uint8_t *, int *) { RSD_NOT_YET("rsd_script_patch_check_batch"); }
 extern "C" int rsd_db_load(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t, int64_t) { RSD_NOT_YET("rsd_db_load"); }
 extern "C" int rsd_db_free(rsd_ctx *) { RSD_NOT_YET("rsd_db_free"); }
 extern "C" int rsd_db_search_topk(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t,
@@ -531,3 +521,221 @@ extern "C" int rsd_db_search_topk_dev(rsd_ctx *, const uint32_t *, const int64_t
                                       uint32_t, int, int, int64_t *, double *, int *, void *) { RSD_NOT_YET("rsd_db_search_topk_dev"); }
 extern "C" int rsd_long_pair(rsd_ctx *, const uint8_t *, int64_t, const uint8_t *, int64_t, int, int, int64_t,
                              uint8_t *, int32_t *, int32_t *, int64_t *, double *, int *) { RSD_NOT_YET("rsd_long_pair"); }
+
+// ------------------------------------------------------------------------------------------------
+// edit scripts + patch (BASELINE config 3)
+// ------------------------------------------------------------------------------------------------
+static int ceil_log2_i64(int64_t v) { int s = 0; while (((int64_t)1 << s) < v) ++s; return s; }
+
+// Shared pipeline: forward (direction codes) -> traceback -> finalize, chunked so the direction
+// words of one chunk fit the device budget.  Device inputs are in c->bufA / c->bufB (and c->bufX).
+int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t n_pairs, int bits, uint32_t symmask,
+                             int force_mode, int64_t max_ops, bool with_x,
+                             uint8_t *op, int32_t *oi, int32_t *oj, int32_t *n_ops, double *dist, uint8_t *ok,
+                             int *mode_out) {
+    cudaStream_t st = stream;
+    const int64_t max_m = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, a_len[i]); return (int64_t)v; }();
+    const int64_t max_n = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, b_len[i]); return (int64_t)v; }();
+    if (max_ops < max_m + max_n && n_pairs > 0) {
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if ((int64_t)a_len[i] + b_len[i] > max_ops)
+                return rsd_fail(RSD_EINVAL, "rsd_script: max_ops (%lld) < m+n (%lld) for pair %lld", (long long)max_ops,
+                                (long long)((int64_t)a_len[i] + b_len[i]), (long long)i);
+    }
+    ModeInfo mi;
+    RSD_OK_OR_RETURN(classify(symmask, max_m, max_n, bits, force_mode == RSD_MODE_I16X2 ? RSD_MODE_I32 : force_mode, mi));
+    int mode = mi.mode == RSD_MODE_I16X2 ? RSD_MODE_I32 : mi.mode;
+    const int S = ceil_log2_i64(max_m + max_n + 66);
+    if (mode == RSD_MODE_I32) {
+        int64_t maxabsw = 0;
+        for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b) maxabsw = std::max<int64_t>(maxabsw, std::llabs((long long)mi.ic.w[a][b]));
+        const double bound = ((double)max_m * mi.ic.del + (double)(max_n + 64) * mi.ic.ins + (double)maxabsw + 2.0) * std::ldexp(1.0, S)
+                             + (double)(max_m + max_n + 66);
+        if (bound >= 2147483000.0) {
+            if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_script: int32 (cost,steps) key would overflow for these lengths");
+            mode = RSD_MODE_F64;
+        }
+    }
+    if (mode_out) *mode_out = mode;
+    if (n_pairs == 0) return RSD_OK;
+    RSD_OK_OR_RETURN(upload_costs(mi, st));
+    const bool f64 = mode == RSD_MODE_F64;
+    const int C = f64 ? 16 : 32;
+
+    // per-pair direction-word counts and chunking
+    size_t free_b = 0, total_b = 0;
+    RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t out_bytes = n_pairs * max_ops * (int64_t)((op ? 1 : 0) + (oi ? 4 : 0) + (oj ? 4 : 0)) + n_pairs * 32;
+    int64_t budget_words = ((int64_t)(free_b * 0.70) - out_bytes) / 4;
+    budget_words = std::min<int64_t>(budget_words, (int64_t)6 << 30);        // <= 24 GiB of direction words per chunk
+    std::vector<int64_t> dir_off((size_t)n_pairs);
+    std::vector<int64_t> chunk_start; chunk_start.push_back(0);
+    int64_t acc = 0, chunk_max_words = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t n_pad = (((int64_t)b_len[p] + C - 1) / C) * C;
+        const int64_t words = (((int64_t)a_len[p] + 15) / 16) * n_pad;
+        const int64_t tmp_bytes_so_far = (p - chunk_start.back() + 1) * max_ops;
+        if (acc > 0 && (acc + words + tmp_bytes_so_far / 4 > budget_words)) {
+            chunk_max_words = std::max(chunk_max_words, acc);
+            chunk_start.push_back(p); acc = 0;
+        }
+        if (words + max_ops / 4 > budget_words)
+            return rsd_fail(RSD_ENOMEM, "rsd_script: pair %lld needs %lld direction words, device budget is %lld", (long long)p,
+                            (long long)words, (long long)budget_words);
+        dir_off[(size_t)p] = acc; acc += words;
+    }
+    chunk_max_words = std::max(chunk_max_words, acc);
+    chunk_start.push_back(n_pairs);
+    int64_t chunk_max_pairs = 0;
+    for (size_t k = 0; k + 1 < chunk_start.size(); ++k) chunk_max_pairs = std::max(chunk_max_pairs, chunk_start[k + 1] - chunk_start[k]);
+
+    RSD_OK_OR_RETURN(dirs.ensure(sizeof(uint32_t) * (size_t)(chunk_max_words + 64)));
+    RSD_OK_OR_RETURN(misc.ensure(sizeof(int64_t) * (size_t)n_pairs));                      // dir_off
+    RSD_OK_OR_RETURN(s_tmp.ensure((size_t)chunk_max_pairs * max_ops + 16));
+    RSD_OK_OR_RETURN(s_nops.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(out_f64.ensure(sizeof(double) * (size_t)n_pairs));
+    if (op) RSD_OK_OR_RETURN(s_op.ensure((size_t)n_pairs * max_ops));
+    if (oi) RSD_OK_OR_RETURN(s_oi.ensure(sizeof(int32_t) * (size_t)n_pairs * max_ops));
+    if (oj) RSD_OK_OR_RETURN(s_oj.ensure(sizeof(int32_t) * (size_t)n_pairs * max_ops));
+    if (ok) RSD_OK_OR_RETURN(s_ok.ensure((size_t)n_pairs));
+    RSD_CUDA(cudaMemcpyAsync(misc.p, dir_off.data(), sizeof(int64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+
+    constexpr int THREADS = 128;
+    const int wpb = THREADS / 32;
+    int blocks = 0;
+    if (f64) { if (bits == 2) RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<true, 2, 16>, THREADS, sm_count, blocks));
+               else RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<true, 4, 16>, THREADS, sm_count, blocks)); }
+    else { if (bits == 2) RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 2, 32>, THREADS, sm_count, blocks));
+           else RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 4, 32>, THREADS, sm_count, blocks)); }
+    const int stride = max_n > 32 * C ? (int)max_m : 0;
+    RSD_OK_OR_RETURN(scratch.ensure((size_t)(f64 ? 12 : 4) * (size_t)stride * blocks * wpb + 64));
+
+    const uint32_t *dA = (const uint32_t *)bufA.words.p, *dB = (const uint32_t *)bufB.words.p;
+    const int64_t *sA = (const int64_t *)bufA.start.p, *sB = (const int64_t *)bufB.start.p;
+    const int32_t *lA = (const int32_t *)bufA.len.p, *lB = (const int32_t *)bufB.len.p;
+    if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+    for (size_t k = 0; k + 1 < chunk_start.size(); ++k) {
+        const int64_t p0 = chunk_start[k], np = chunk_start[k + 1] - p0;
+        SeqView A{dA, sA + p0, lA + p0}, B{dB, sB + p0, lB + p0};
+        PlanView pv;
+        // trivial pairs (m == 0 or n == 0) get their distance from the planner and an all-INS / all-DEL script from the traceback
+        RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv));
+        ScriptView sv{(uint32_t *)dirs.p, (const int64_t *)misc.p + p0, (double *)out_f64.p + p0};
+        if (f64) {
+            if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+            else k_script_fwd<true, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+        } else {
+            if (bits == 2) k_script_fwd<false, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+            else k_script_fwd<false, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+        }
+        k_traceback<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(lA + p0, lB + p0, np, (const uint32_t *)dirs.p,
+                                                               (const int64_t *)misc.p + p0, C, (uint8_t *)s_tmp.p, max_ops,
+                                                               (int32_t *)s_nops.p + p0);
+        FinalizeArgs fa{};
+        fa.tmp = (const uint8_t *)s_tmp.p; fa.max_ops = max_ops; fa.n_ops = (const int32_t *)s_nops.p + p0; fa.end_aligned = 1;
+        fa.A = A; fa.B = B; fa.bits = bits;
+        fa.X = with_x ? SeqView{(const uint32_t *)bufX.words.p, (const int64_t *)bufX.start.p + p0, (const int32_t *)bufX.len.p + p0} : A;
+        fa.op = op ? (uint8_t *)s_op.p + p0 * max_ops : nullptr;
+        fa.oi = oi ? (int32_t *)s_oi.p + p0 * max_ops : nullptr;
+        fa.oj = oj ? (int32_t *)s_oj.p + p0 * max_ops : nullptr;
+        fa.out_stride = max_ops;
+        fa.patched = nullptr; fa.max_out = 0; fa.out_len = nullptr; fa.err = nullptr;
+        fa.ok = ok ? (uint8_t *)s_ok.p + p0 : nullptr;
+        if (op || oi || oj || ok) { k_finalize<<<(unsigned)np, 256, 0, st>>>(fa, np); launches += 1; }
+        launches += 2;
+        RSD_CUDA(cudaGetLastError());
+    }
+    if (timing) { RSD_CUDA(cudaEventRecord(ev1, st)); timed = true; }
+    if (op) RSD_CUDA(cudaMemcpyAsync(op, s_op.p, (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+    if (oi) RSD_CUDA(cudaMemcpyAsync(oi, s_oi.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+    if (oj) RSD_CUDA(cudaMemcpyAsync(oj, s_oj.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+    if (n_ops) RSD_CUDA(cudaMemcpyAsync(n_ops, s_nops.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (dist) RSD_CUDA(cudaMemcpyAsync(dist, out_f64.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (ok) RSD_CUDA(cudaMemcpyAsync(ok, s_ok.p, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaStreamSynchronize(st));
+    return RSD_OK;
+}
+
+static int script_common(rsd_ctx *c, const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
+                         const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
+                         int64_t n_pairs, int bits, uint32_t symmask, int force_mode, int64_t max_ops,
+                         uint8_t *op, int32_t *oi, int32_t *oj, int32_t *n_ops, double *dist, uint8_t *ok, int *mode_out) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_pairs < 0 || n_pairs > INT32_MAX) return rsd_fail(RSD_EINVAL, "rsd_script: n_pairs out of range");
+    if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
+    if (n_pairs > 0 && (!a_words || !a_start || !a_len || !b_words || !b_start || !b_len))
+        return rsd_fail(RSD_EINVAL, "rsd_script: NULL input buffer");
+    if (max_ops < 1) return rsd_fail(RSD_EINVAL, "rsd_script: max_ops must be >= 1");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (n_pairs == 0) { if (mode_out) *mode_out = 0; return RSD_OK; }
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufA, a_words, a_start, a_len, n_pairs, a_nwords, c->stream));
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufB, b_words, b_start, b_len, n_pairs, b_nwords, c->stream));
+    return c->script_pipeline(a_len, b_len, n_pairs, bits, symmask, force_mode, max_ops, false, op, oi, oj, n_ops, dist, ok, mode_out);
+}
+
+extern "C" int rsd_script_batch(rsd_ctx *c,
+                                const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
+                                const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
+                                int64_t n_pairs, int bits, uint32_t symmask, int force_mode, int64_t max_ops,
+                                uint8_t *op, int32_t *oi, int32_t *oj, int32_t *n_ops, double *dist, int *mode_out) {
+    return script_common(c, a_words, a_start, a_len, a_nwords, b_words, b_start, b_len, b_nwords, n_pairs, bits, symmask,
+                         force_mode, max_ops, op, oi, oj, n_ops, dist, nullptr, mode_out);
+}
+
+extern "C" int rsd_script_patch_check_batch(rsd_ctx *c,
+                                const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
+                                const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
+                                int64_t n_pairs, int bits, uint32_t symmask, int force_mode, int64_t max_ops,
+                                uint8_t *op, int32_t *oi, int32_t *oj, int32_t *n_ops, double *dist, uint8_t *ok, int *mode_out) {
+    if (!ok) return rsd_fail(RSD_EINVAL, "rsd_script_patch_check_batch: ok is NULL");
+    return script_common(c, a_words, a_start, a_len, a_nwords, b_words, b_start, b_len, b_nwords, n_pairs, bits, symmask,
+                         force_mode, max_ops, op, oi, oj, n_ops, dist, ok, mode_out);
+}
+
+extern "C" int rsd_patch_batch(rsd_ctx *c,
+                               const uint8_t *op, const int32_t *oi, const int32_t *oj, const int32_t *n_ops, int64_t max_ops,
+                               const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
+                               const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
+                               const uint32_t *x_words, const int64_t *x_start, const int32_t *x_len, int64_t x_nwords,
+                               int64_t n_pairs, int bits, int64_t max_out, uint8_t *out, int32_t *out_len, int32_t *err) {
+    (void)oi; (void)oj;        // derivable from op (prefix sums); accepted for symmetry with rsd_script_batch
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_pairs < 0) return rsd_fail(RSD_EINVAL, "rsd_patch_batch: n_pairs < 0");
+    if (n_pairs > 0 && (!op || !n_ops || !a_words || !b_words || !x_words || !out || !out_len || !err))
+        return rsd_fail(RSD_EINVAL, "rsd_patch_batch: NULL buffer");
+    if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (n_pairs == 0) return RSD_OK;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (n_ops[p] < 0 || n_ops[p] > max_ops) return rsd_fail(RSD_EINVAL, "rsd_patch_batch: n_ops[%lld] out of range", (long long)p);
+        if ((int64_t)x_len[p] + b_len[p] > max_out) return rsd_fail(RSD_EINVAL, "rsd_patch_batch: max_out too small for pair %lld", (long long)p);
+    }
+    cudaStream_t st = c->stream;
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufA, a_words, a_start, a_len, n_pairs, a_nwords, st));
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufB, b_words, b_start, b_len, n_pairs, b_nwords, st));
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufX, x_words, x_start, x_len, n_pairs, x_nwords, st));
+    RSD_OK_OR_RETURN(c->s_tmp.ensure((size_t)n_pairs * max_ops + 16));
+    RSD_OK_OR_RETURN(c->s_nops.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(c->p_out.ensure((size_t)n_pairs * max_out + 16));
+    RSD_OK_OR_RETURN(c->p_len.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(c->p_err.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    RSD_CUDA(cudaMemcpyAsync(c->s_tmp.p, op, (size_t)n_pairs * max_ops, cudaMemcpyHostToDevice, st));
+    RSD_CUDA(cudaMemcpyAsync(c->s_nops.p, n_ops, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+    RSD_CUDA(cudaMemsetAsync(c->p_out.p, 0, (size_t)n_pairs * max_out, st));
+    FinalizeArgs fa{};
+    fa.tmp = (const uint8_t *)c->s_tmp.p; fa.max_ops = max_ops; fa.n_ops = (const int32_t *)c->s_nops.p; fa.end_aligned = 0;
+    fa.A = SeqView{(const uint32_t *)c->bufA.words.p, (const int64_t *)c->bufA.start.p, (const int32_t *)c->bufA.len.p};
+    fa.B = SeqView{(const uint32_t *)c->bufB.words.p, (const int64_t *)c->bufB.start.p, (const int32_t *)c->bufB.len.p};
+    fa.X = SeqView{(const uint32_t *)c->bufX.words.p, (const int64_t *)c->bufX.start.p, (const int32_t *)c->bufX.len.p};
+    fa.bits = bits; fa.op = nullptr; fa.oi = nullptr; fa.oj = nullptr; fa.out_stride = max_ops;
+    fa.patched = (uint8_t *)c->p_out.p; fa.max_out = max_out; fa.out_len = (int32_t *)c->p_len.p; fa.err = (int32_t *)c->p_err.p;
+    fa.ok = nullptr;
+    k_finalize<<<(unsigned)n_pairs, 256, 0, st>>>(fa, n_pairs);
+    c->launches += 1;
+    RSD_CUDA(cudaGetLastError());
+    RSD_CUDA(cudaMemcpyAsync(out, c->p_out.p, (size_t)n_pairs * max_out, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaMemcpyAsync(out_len, c->p_len.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaMemcpyAsync(err, c->p_err.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaStreamSynchronize(st));
+    return RSD_OK;
+}

@@ -75,7 +75,7 @@ struct rsd_ctx {
     DevBuf out_f64, scratch, plan_pair_bin, plan_bins, plan_groups;
     DevBuf mat_vals, mat_mask, mat_ab;
     // script / patch
-    DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, p_out, p_len, p_err, misc;
+    DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, s_tmp, p_out, p_len, p_err, misc;
     // database shard
     SeqBufs db;
     int64_t db_n = 0, db_base = 0, db_nwords = 0, db_maxlen = 0;
@@ -93,10 +93,13 @@ struct rsd_ctx {
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
+    int script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t n_pairs, int bits, uint32_t symmask,
+                        int force_mode, int64_t max_ops, bool with_x, uint8_t *op, int32_t *oi, int32_t *oj,
+                        int32_t *n_ops, double *dist, uint8_t *ok, int *mode_out);
     void free_all() {
         bufA.release(); bufB.release(); bufX.release(); bufQ.release(); db.release();
         DevBuf *all[] = {&out_f64, &scratch, &plan_pair_bin, &plan_bins, &plan_groups, &mat_vals, &mat_mask, &mat_ab,
-                         &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &p_out, &p_len, &p_err, &misc,
+                         &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
                          &db_dist, &db_topi, &db_tops, &db_aux};
         for (DevBuf *b : all) b->release();
     }

@@ -1,0 +1,251 @@
+// k_search.cuh — query batch vs resident database shard with exact top-k (BASELINE config 5).
+//
+// Replaces (reference): the wf_score scan of search_collection IR:466-477 (one wagnerFisher per
+// document, IR:435-440) and the stable descending sort + [:k] of performance.py:12-15.
+//
+// Fast kernel (records <= 32 symbols, <= 7 distinct symbols incl. the queries', dyadic costs):
+//   one thread = two database records (lo / hi half of every register, int16 H' values), the
+//   record right-aligned in 32 column registers and left-padded with a PAD symbol whose w >= 0
+//   keeps H' at the border value 0 — so the answer is always in column register 31.
+//   The query symbol of a row is uniform over the whole grid: its 8-byte row of the compact cost
+//   table comes from shared memory with one broadcast LDS.64, and each packed cell is
+//   PRMT (both records' w, sign-extended) + VIADDMNMX.S16x2 + VIMNMX.S16x2.
+//   The record's selector registers are built once and reused for every query of the batch.
+// Top-k: a candidate passes when its key (score desc, global index asc) is not worse than the
+//   current k-th best key of its query (tau).  tau starts at "accept all" and is tightened after
+//   every chunk by k_topk_fold, which also keeps the running top-k list.  The final order is a
+//   total order on (score, index), so the result does not depend on atomic ordering.
+#pragma once
+#include "k_dist.cuh"
+
+#define RSD_TOPK_MAX 128
+
+struct SearchTab {               // per query-batch constants
+    int ins, del;                // scaled
+    double inv_scale;
+    uint32_t compact_lut_lo, compact_lut_hi;   // 16 x 4-bit: original code -> compact index (7 = PAD / absent)
+};
+
+struct TopkState {
+    double *tau_s; int64_t *tau_i;         // [Q] current k-th best key (score, index); index LLONG_MAX = accept all on ties
+    double *best_s; int64_t *best_i;       // [Q][k] running top-k, sorted
+    double *cand_s; int64_t *cand_i;       // [Q][cap] candidates of the current chunk
+    int *cand_n;                           // [Q]
+    int64_t cap;
+    int k;
+};
+
+// rowtab[q][i] = 8 bytes: (int8) w(query symbol i of q, compact symbol 0..7); byte 7 (PAD) = +127
+__global__ void __launch_bounds__(128)
+k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_start,
+                const int32_t *__restrict__ db_len, int64_t rec0, int64_t n_rec, int db_bits, int64_t global_base,
+                const uint2 *__restrict__ rowtab, int QROWS, const int32_t *__restrict__ q_len, int n_queries,
+                SearchTab tab, TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *s_rows = reinterpret_cast<uint2 *>(smem_raw);                     // [n_queries][QROWS]
+    double *s_tau = reinterpret_cast<double *>(s_rows + (size_t)n_queries * QROWS);
+    long long *s_taui = reinterpret_cast<long long *>(s_tau + n_queries);
+    int *s_qlen = reinterpret_cast<int *>(s_taui + n_queries);
+    for (int k = threadIdx.x; k < n_queries * QROWS; k += blockDim.x) s_rows[k] = rowtab[k];
+    for (int k = threadIdx.x; k < n_queries; k += blockDim.x) {
+        s_tau[k] = tk.tau_s[k]; s_taui[k] = tk.tau_i[k]; s_qlen[k] = q_len[k];
+    }
+    __syncthreads();
+
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t rA = rec0 + 2 * t, rB = rA + 1;
+    if (rA >= rec0 + n_rec) return;
+    const bool hasB = rB < rec0 + n_rec;
+    const int nA = db_len[rA], nB = hasB ? db_len[rB] : nA;
+    const uint32_t *wA = db_words + db_start[rA];
+    const uint32_t *wB = hasB ? db_words + db_start[rB] : wA;
+    const uint64_t lut = ((uint64_t)tab.compact_lut_hi << 32) | tab.compact_lut_lo;
+
+    // selectors: nibbles [idx A][8|idx A -> sign][idx B][8|idx B -> sign], both index the same 8-byte row
+    uint32_t sel[32];
+    {
+        const int per = 32 / db_bits;
+        uint32_t cwA = 0, cwB = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int jA = c - (32 - nA), jB = c - (32 - nB);
+            uint32_t ia = 7u, ib = 7u;                                       // PAD
+            if (jA >= 0) {
+                if (jA % per == 0 || c == 32 - nA) cwA = __ldg(wA + jA / per);
+                const uint32_t code = (cwA >> ((jA % per) * db_bits)) & ((1u << db_bits) - 1u);
+                ia = (uint32_t)(lut >> (4 * code)) & 7u;
+            }
+            if (jB >= 0) {
+                if (jB % per == 0 || c == 32 - nB) cwB = __ldg(wB + jB / per);
+                const uint32_t code = (cwB >> ((jB % per) * db_bits)) & ((1u << db_bits) - 1u);
+                ib = (uint32_t)(lut >> (4 * code)) & 7u;
+            }
+            sel[c] = 0x8080u + ia * 0x11u + ib * 0x1100u;
+        }
+    }
+    const int baseA = nA * tab.ins, baseB = nB * tab.ins;
+
+    for (int q = 0; q < n_queries; ++q) {
+        uint32_t H[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) H[c] = 0u;
+        const int m = s_qlen[q];
+        const uint2 *rows = s_rows + (size_t)q * QROWS;
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) {
+            const uint2 r = rows[i];
+            uint32_t left = 0u, diag = 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const uint32_t w = prmt(r.x, r.y, sel[c]);
+                const uint32_t t2 = addmin16x2(diag, w, H[c]);
+                diag = H[c];
+                H[c] = min16x2(t2, left);
+                left = H[c];
+            }
+        }
+        const int dA = (int)(int16_t)(H[31] & 0xffffu) + m * tab.del + baseA;
+        const int dB = (int)(int16_t)(H[31] >> 16) + m * tab.del + baseB;
+        // IR:440  score = 1 / (1 + cost)
+        const double sA = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dA, tab.inv_scale)));
+        const double sB = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dB, tab.inv_scale)));
+        if (all_scores) {
+            all_scores[(size_t)q * all_stride + rA] = sA;
+            if (hasB) all_scores[(size_t)q * all_stride + rB] = sB;
+        }
+        if (tk.k > 0) {
+            const double ts = s_tau[q]; const long long ti = s_taui[q];
+            const long long gA = global_base + rA, gB = global_base + rB;
+            if (sA > ts || (sA == ts && gA <= ti)) {
+                const int slot = atomicAdd(&tk.cand_n[q], 1);
+                if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
+            }
+            if (hasB && (sB > ts || (sB == ts && gB <= ti))) {
+                const int slot = atomicAdd(&tk.cand_n[q], 1);
+                if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sB; tk.cand_i[(size_t)q * tk.cap + slot] = gB; }
+            }
+        }
+    }
+}
+
+// General path: distances of one query against a range of records were produced by the systolic
+// distance kernels (any mode); turn them into scores, optional all_scores row, and candidates.
+__global__ void k_score_filter(const double *__restrict__ dist, int64_t rec0, int64_t n_rec, int64_t global_base, int q,
+                               TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const double s = __ddiv_rn(1.0, __dadd_rn(1.0, dist[r]));
+    if (all_scores) all_scores[(size_t)q * all_stride + rec0 + r] = s;
+    if (tk.k > 0) {
+        const double ts = tk.tau_s[q]; const long long ti = tk.tau_i[q];
+        const long long g = global_base + rec0 + r;
+        if (s > ts || (s == ts && g <= ti)) {
+            const int slot = atomicAdd(&tk.cand_n[q], 1);
+            if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = s; tk.cand_i[(size_t)q * tk.cap + slot] = g; }
+        }
+    }
+}
+
+__global__ void k_topk_init(TopkState tk, int n_queries) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    tk.tau_s[q] = -1.0; tk.tau_i[q] = 0x7fffffffffffffffLL;      // accept everything (scores are > 0)
+    tk.cand_n[q] = 0;
+    for (int r = 0; r < tk.k; ++r) { tk.best_s[(size_t)q * tk.k + r] = 0.0; tk.best_i[(size_t)q * tk.k + r] = -1; }
+}
+
+// key order: a before b  <=>  score_a > score_b, or equal scores and index_a < index_b
+__device__ __forceinline__ bool key_before(double sa, long long ia, double sb, long long ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+// One CTA per query: merge this chunk's candidates into the running sorted top-k, update tau.
+// k rounds of "best remaining candidate" (block argbest), each inserted into the sorted list.
+__global__ void __launch_bounds__(256) k_topk_fold(TopkState tk) {
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ double s_bs[RSD_TOPK_MAX]; __shared__ long long s_bi[RSD_TOPK_MAX];
+    __shared__ double r_s[256]; __shared__ long long r_i[256]; __shared__ int r_pos[256];
+    const int k = tk.k;
+    const int n = (int)min((int64_t)tk.cand_n[q], tk.cap);
+    for (int r = tid; r < k; r += 256) { s_bs[r] = tk.best_s[(size_t)q * k + r]; s_bi[r] = tk.best_i[(size_t)q * k + r]; }
+    __syncthreads();
+    double *cs = tk.cand_s + (size_t)q * tk.cap; int64_t *ci = tk.cand_i + (size_t)q * tk.cap;
+    for (int round = 0; round < k; ++round) {
+        // best remaining candidate (taken ones are marked with index -2)
+        double bs = -2.0; long long bi = 0x7fffffffffffffffLL; int bp = -1;
+        for (int c = tid; c < n; c += 256) {
+            const long long idx = ci[c];
+            if (idx == -2) continue;
+            const double s = cs[c];
+            if (bp < 0 || key_before(s, idx, bs, bi)) { bs = s; bi = idx; bp = c; }
+        }
+        r_s[tid] = bs; r_i[tid] = bi; r_pos[tid] = bp;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) {
+                const int ob = r_pos[tid + o];
+                if (ob >= 0 && (r_pos[tid] < 0 || key_before(r_s[tid + o], r_i[tid + o], r_s[tid], r_i[tid]))) {
+                    r_s[tid] = r_s[tid + o]; r_i[tid] = r_i[tid + o]; r_pos[tid] = ob;
+                }
+            }
+            __syncthreads();
+        }
+        const int wp = r_pos[0];
+        if (wp < 0) break;                                   // no candidates left
+        const double ws = r_s[0]; const long long wi = r_i[0];
+        __syncthreads();
+        // insert into the sorted list if it beats the current last entry (or the list has a free slot)
+        const bool list_full = s_bi[k - 1] >= 0;
+        const bool better = !list_full || key_before(ws, wi, s_bs[k - 1], s_bi[k - 1]);
+        __syncthreads();
+        if (!better) break;                                  // candidates come out best-first: nothing further can enter
+        if (tid == 0) {
+            ci[wp] = -2;
+            // duplicates (same global index already in the list) cannot occur: every record is scanned once
+            int pos = k - 1;
+            while (pos > 0 && (s_bi[pos - 1] < 0 || key_before(ws, wi, s_bs[pos - 1], s_bi[pos - 1]))) {
+                s_bs[pos] = s_bs[pos - 1]; s_bi[pos] = s_bi[pos - 1]; --pos;
+            }
+            s_bs[pos] = ws; s_bi[pos] = wi;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int r = tid; r < k; r += 256) { tk.best_s[(size_t)q * k + r] = s_bs[r]; tk.best_i[(size_t)q * k + r] = s_bi[r]; }
+    if (tid == 0) {
+        tk.cand_n[q] = 0;
+        if (s_bi[k - 1] >= 0) { tk.tau_s[q] = s_bs[k - 1]; tk.tau_i[q] = s_bi[k - 1]; }
+    }
+}
+
+
+// rowtab[q][i] from the packed queries: byte b < 7 = (int8) w(query symbol, compact symbol b), byte 7 = +127 (PAD)
+__global__ void k_build_rowtab(const uint32_t *__restrict__ q_words, const int64_t *__restrict__ q_start,
+                               const int32_t *__restrict__ q_len, int n_queries, int bits, int QROWS,
+                               const IntCosts *__restrict__ ic, uint32_t compact_syms_lo, uint32_t compact_syms_hi,
+                               uint2 *__restrict__ rowtab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_queries * QROWS) return;
+    const int q = idx / QROWS, i = idx % QROWS;
+    uint2 r = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+    if (i < q_len[q]) {
+        const uint32_t a = pk_get(q_words, q_start[q], i, bits);
+        const uint64_t syms = ((uint64_t)compact_syms_hi << 32) | compact_syms_lo;   // 7 x 4-bit original codes
+        uint64_t v = 0;
+        for (int b = 0; b < 7; ++b) {
+            const uint32_t sym = (uint32_t)(syms >> (4 * b)) & 15u;
+            v |= (uint64_t)(uint8_t)(int8_t)ic->w[a][sym] << (8 * b);
+        }
+        v |= (uint64_t)0x7f << 56;
+        r = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+    }
+    rowtab[idx] = r;
+}
+
+__global__ void k_fill_query_view(const int64_t *__restrict__ q_start, const int32_t *__restrict__ q_len, int q,
+                                  int64_t n, int64_t *__restrict__ a_start, int32_t *__restrict__ a_len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    a_start[r] = q_start[q]; a_len[r] = q_len[q];
+}

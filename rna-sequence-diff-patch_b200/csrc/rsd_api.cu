@@ -14,6 +14,7 @@
 #include "k_matrix.cuh"
 #include "k_ubench.cuh"
 #include "k_script.cuh"
+#include "k_search.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -193,6 +194,7 @@ int rsd_ctx::classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, 
     else return rsd_fail(RSD_EINVAL, "rsd: unknown force_mode %d", force_mode);
     mi.mode = mode;
     mi.k = k < 0 ? 0 : k;
+    mi.dyadic = k >= 0; mi.i16_ok = i16_ok; mi.i32_ok = i32_ok;
     return RSD_OK;
 }
 
@@ -513,12 +515,6 @@ extern "C" int rsd_topk_merge(const int64_t *idx, const double *score, int n_sha
 }
 
 #include "rsd_stubs.cuh"
-extern "C" int rsd_db_load(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t, int64_t) { RSD_NOT_YET("rsd_db_load"); }
-extern "C" int rsd_db_free(rsd_ctx *) { RSD_NOT_YET("rsd_db_free"); }
-extern "C" int rsd_db_search_topk(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int, uint32_t,
-                                  int, int, int64_t *, double *, double *, int *) { RSD_NOT_YET("rsd_db_search_topk"); }
-extern "C" int rsd_db_search_topk_dev(rsd_ctx *, const uint32_t *, const int64_t *, const int32_t *, int64_t, int64_t, int,
-                                      uint32_t, int, int, int64_t *, double *, int *, void *) { RSD_NOT_YET("rsd_db_search_topk_dev"); }
 extern "C" int rsd_long_pair(rsd_ctx *, const uint8_t *, int64_t, const uint8_t *, int64_t, int, int, int64_t,
                              uint8_t *, int32_t *, int32_t *, int64_t *, double *, int *) { RSD_NOT_YET("rsd_long_pair"); }
 
@@ -736,6 +732,177 @@ extern "C" int rsd_patch_batch(rsd_ctx *c,
     RSD_CUDA(cudaMemcpyAsync(out, c->p_out.p, (size_t)n_pairs * max_out, cudaMemcpyDeviceToHost, st));
     RSD_CUDA(cudaMemcpyAsync(out_len, c->p_len.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     RSD_CUDA(cudaMemcpyAsync(err, c->p_err.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaStreamSynchronize(st));
+    return RSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// database search (BASELINE config 5)
+// ------------------------------------------------------------------------------------------------
+extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *start, const int32_t *len,
+                           int64_t n_records, int64_t n_words, int bits, uint32_t symmask, int64_t global_index_base) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_records < 0 || (n_records > 0 && (!words || !start || !len))) return rsd_fail(RSD_EINVAL, "rsd_db_load: bad arguments");
+    if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
+    if (bits == 2 && (symmask & ~0xFu)) return rsd_fail(RSD_EINVAL, "rsd_db_load: 2-bit packing with symbols outside ACGU");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    RSD_OK_OR_RETURN(c->upload_seqs(c->db, words, start, len, n_records, n_words, c->stream));
+    RSD_CUDA(cudaStreamSynchronize(c->stream));
+    c->db_n = n_records; c->db_base = global_index_base; c->db_nwords = n_words; c->db_bits = bits; c->db_symmask = symmask;
+    int32_t mx = 0;
+    for (int64_t i = 0; i < n_records; ++i) mx = std::max(mx, len[i]);
+    c->db_maxlen = mx;
+    c->db_loaded = true;
+    return RSD_OK;
+}
+
+extern "C" int rsd_db_free(rsd_ctx *c) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); }
+    c->db_loaded = false; c->db_n = 0;
+    return RSD_OK;
+}
+
+// queries already on the device; outputs to device buffers (top_idx/top_score [Q][k]) and optionally all scores
+int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len, int64_t n_queries,
+                        int64_t max_qlen, int bits, uint32_t q_symmask, int k, int force_mode,
+                        int64_t *top_idx, double *top_score, double *all_scores_dev, int *mode_out, cudaStream_t st) {
+    if (!db_loaded) return rsd_fail(RSD_EINVAL, "rsd_db_search: no database loaded (rsd_db_load)");
+    if (bits != db_bits) return rsd_fail(RSD_EINVAL, "rsd_db_search: query packing (%d bit) differs from the database (%d bit)", bits, db_bits);
+    if (k < 0 || k > RSD_TOPK_MAX) return rsd_fail(RSD_EINVAL, "rsd_db_search: k must be in 0..%d (ask for all_scores instead)", RSD_TOPK_MAX);
+    if (n_queries < 0 || n_queries > 1 << 20) return rsd_fail(RSD_EINVAL, "rsd_db_search: n_queries out of range");
+    const uint32_t symmask = db_symmask | q_symmask;
+    ModeInfo mi;
+    RSD_OK_OR_RETURN(classify(symmask, max_qlen, db_maxlen, bits, force_mode == RSD_MODE_I16X2 ? 0 : force_mode, mi));
+    timed = false;
+    // fast path applicability
+    int nsym = 0; uint32_t syms_lo = 0, syms_hi = 0, lut_lo = 0x77777777u, lut_hi = 0x77777777u;
+    bool w8 = true;
+    for (int a = 0; a < 16; ++a) if (symmask >> a & 1) {
+        if (nsym < 7) {
+            if (nsym < 8) { uint64_t s64 = ((uint64_t)syms_hi << 32) | syms_lo; s64 |= (uint64_t)a << (4 * nsym); syms_lo = (uint32_t)s64; syms_hi = (uint32_t)(s64 >> 32); }
+            uint64_t l64 = ((uint64_t)lut_hi << 32) | lut_lo; l64 &= ~((uint64_t)15 << (4 * a)); l64 |= (uint64_t)nsym << (4 * a);
+            lut_lo = (uint32_t)l64; lut_hi = (uint32_t)(l64 >> 32);
+        }
+        ++nsym;
+    }
+    if (mi.dyadic)
+        for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b)
+            if ((symmask >> a & 1) && (symmask >> b & 1) && (mi.ic.w[a][b] < -128 || mi.ic.w[a][b] > 126)) w8 = false;
+    const int QROWS = (int)((max_qlen + 7) / 8 * 8);
+    const bool fast = mi.dyadic && mi.i16_ok && w8 && nsym <= 7 && db_maxlen <= 32 && max_qlen >= 1 && QROWS <= 64 &&
+                      (force_mode == 0 || force_mode == RSD_MODE_I16X2);
+    if (force_mode == RSD_MODE_I16X2 && !fast) return rsd_fail(RSD_EINVAL, "rsd_db_search: int16x2 search kernel not applicable (symbols, costs or lengths)");
+    if (mode_out) *mode_out = fast ? RSD_MODE_I16X2 : mi.mode;
+    if (n_queries == 0) return RSD_OK;
+    RSD_OK_OR_RETURN(upload_costs(mi, st));
+
+    // chunking: a small first chunk seeds tau cheaply, then large ones; candidate capacity = chunk size
+    const int64_t CH0 = 32768, CH = (int64_t)1 << 20;
+    const int QB = fast ? 64 : 16;                           // queries per batch
+    const int64_t cap = std::min<int64_t>(std::max<int64_t>(db_n, 1), CH);
+    const size_t per_q = (size_t)cap * 16 + (size_t)std::max(k, 1) * 16 + 64;
+    RSD_OK_OR_RETURN(db_aux.ensure(per_q * QB + (size_t)QB * 64 * 8 + 4096));
+    RSD_OK_OR_RETURN(db_topi.ensure((size_t)QB * QROWS * 8 + 64));
+    unsigned char *aux = (unsigned char *)db_aux.p;
+    TopkState tk{};
+    tk.k = k; tk.cap = cap;
+    tk.cand_s = (double *)aux; aux += (size_t)QB * cap * 8;
+    tk.cand_i = (int64_t *)aux; aux += (size_t)QB * cap * 8;
+    tk.best_s = (double *)aux; aux += (size_t)QB * std::max(k, 1) * 8;
+    tk.best_i = (int64_t *)aux; aux += (size_t)QB * std::max(k, 1) * 8;
+    tk.tau_s = (double *)aux; aux += (size_t)QB * 8;
+    tk.tau_i = (int64_t *)aux; aux += (size_t)QB * 8;
+    tk.cand_n = (int *)aux; aux += (size_t)QB * 4;
+    uint2 *rowtab = (uint2 *)db_topi.p;
+    if (!fast) {
+        RSD_OK_OR_RETURN(db_dist.ensure((size_t)cap * 8 + 64));
+        RSD_OK_OR_RETURN(db_tops.ensure((size_t)cap * 12 + 64));
+    }
+    SearchTab tab{};
+    tab.ins = mi.ic.ins; tab.del = mi.ic.del; tab.inv_scale = 1.0 / (double)(1 << mi.ic.scale_log2);
+    tab.compact_lut_lo = lut_lo; tab.compact_lut_hi = lut_hi;
+    const uint32_t *dbw = (const uint32_t *)db.words.p; const int64_t *dbs = (const int64_t *)db.start.p; const int32_t *dbl = (const int32_t *)db.len.p;
+    if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+    for (int64_t q0 = 0; q0 < n_queries; q0 += QB) {
+        const int nq = (int)std::min<int64_t>(QB, n_queries - q0);
+        if (k > 0) { k_topk_init<<<(nq + 63) / 64, 64, 0, st>>>(tk, nq); launches += 1; }
+        if (fast) {
+            k_build_rowtab<<<(nq * QROWS + 127) / 128, 128, 0, st>>>(q_words, q_start + q0, q_len + q0, nq, bits, QROWS, d_ic, syms_lo, syms_hi, rowtab);
+            launches += 1;
+        }
+        for (int64_t r0 = 0; r0 < db_n;) {
+            const int64_t nr = std::min<int64_t>(r0 == 0 ? std::min(CH0, cap) : cap, db_n - r0);
+            double *alls = all_scores_dev ? all_scores_dev + (size_t)q0 * db_n : nullptr;
+            if (fast) {
+                const int64_t threads = (nr + 1) / 2;
+                const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
+                k_search_twin16<<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, db_base, rowtab, QROWS,
+                                                                                      q_len + q0, nq, tab, tk, alls, db_n);
+                launches += 1;
+            } else {
+                for (int q = 0; q < nq; ++q) {
+                    k_fill_query_view<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(q_start + q0, q_len + q0, q, nr, (int64_t *)db_tops.p,
+                                                                                     (int32_t *)((int64_t *)db_tops.p + cap));
+                    launches += 1;
+                    int mode_unused = 0;
+                    const bool t_save = timing; timing = false;
+                    int rc = distance_dev(q_words, (const int64_t *)db_tops.p, (const int32_t *)((int64_t *)db_tops.p + cap), dbw, dbs + r0,
+                                          dbl + r0, nr, max_qlen, db_maxlen, bits, symmask, force_mode, (double *)db_dist.p, &mode_unused, st);
+                    timing = t_save;
+                    if (rc) return rc;
+                    k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, db_base, q, tk, alls, db_n);
+                    launches += 1;
+                }
+            }
+            if (k > 0) { k_topk_fold<<<nq, 256, 0, st>>>(tk); launches += 1; }
+            RSD_CUDA(cudaGetLastError());
+            r0 += nr;
+        }
+        if (k > 0) {
+            RSD_CUDA(cudaMemcpyAsync(top_idx + q0 * k, tk.best_i, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToDevice, st));
+            RSD_CUDA(cudaMemcpyAsync(top_score + q0 * k, tk.best_s, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (timing) { RSD_CUDA(cudaEventRecord(ev1, st)); timed = true; }
+    return RSD_OK;
+}
+
+extern "C" int rsd_db_search_topk_dev(rsd_ctx *c, const uint32_t *q_words_dev, const int64_t *q_start_dev,
+                                      const int32_t *q_len_dev, int64_t n_queries, int64_t max_qlen, int bits,
+                                      uint32_t q_symmask, int k, int force_mode,
+                                      int64_t *top_idx_dev, double *top_score_dev, int *mode_out, void *stream) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (k < 1) return rsd_fail(RSD_EINVAL, "rsd_db_search_topk_dev: k must be >= 1");
+    return c->search_dev(q_words_dev, q_start_dev, q_len_dev, n_queries, max_qlen, bits, q_symmask, k, force_mode,
+                         top_idx_dev, top_score_dev, nullptr, mode_out, (cudaStream_t)stream);
+}
+
+extern "C" int rsd_db_search_topk(rsd_ctx *c, const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len,
+                                  int64_t n_queries, int64_t q_nwords, int bits, uint32_t q_symmask, int k, int force_mode,
+                                  int64_t *top_idx, double *top_score, double *all_scores, int *mode_out) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_queries < 0 || (n_queries > 0 && (!q_words || !q_start || !q_len))) return rsd_fail(RSD_EINVAL, "rsd_db_search_topk: bad arguments");
+    if (k > 0 && (!top_idx || !top_score)) return rsd_fail(RSD_EINVAL, "rsd_db_search_topk: NULL top-k output");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (n_queries == 0) return RSD_OK;
+    cudaStream_t st = c->stream;
+    RSD_OK_OR_RETURN(c->upload_seqs(c->bufQ, q_words, q_start, q_len, n_queries, q_nwords, st));
+    const int kk = std::max(k, 0);
+    RSD_OK_OR_RETURN(c->s_oi.ensure(sizeof(int64_t) * (size_t)n_queries * std::max(kk, 1)));
+    RSD_OK_OR_RETURN(c->s_oj.ensure(sizeof(double) * (size_t)n_queries * std::max(kk, 1)));
+    if (all_scores) RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_queries * std::max<int64_t>(c->db_n, 1)));
+    int64_t max_qlen = 0;
+    for (int64_t i = 0; i < n_queries; ++i) max_qlen = std::max<int64_t>(max_qlen, q_len[i]);
+    RSD_OK_OR_RETURN(c->search_dev((const uint32_t *)c->bufQ.words.p, (const int64_t *)c->bufQ.start.p, (const int32_t *)c->bufQ.len.p,
+                                   n_queries, max_qlen, bits, q_symmask, kk, force_mode, (int64_t *)c->s_oi.p, (double *)c->s_oj.p,
+                                   all_scores ? (double *)c->out_f64.p : nullptr, mode_out, st));
+    if (kk > 0) {
+        RSD_CUDA(cudaMemcpyAsync(top_idx, c->s_oi.p, sizeof(int64_t) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
+        RSD_CUDA(cudaMemcpyAsync(top_score, c->s_oj.p, sizeof(double) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
+    }
+    if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores, c->out_f64.p, sizeof(double) * (size_t)n_queries * c->db_n, cudaMemcpyDeviceToHost, st));
     RSD_CUDA(cudaStreamSynchronize(st));
     return RSD_OK;
 }

@@ -54,6 +54,7 @@ struct ModeInfo {
     int k;          // scale_log2 (int modes)
     IntCosts ic;
     F64Costs fc;
+    bool dyadic, i16_ok, i32_ok;
 };
 
 struct rsd_ctx {
@@ -81,6 +82,7 @@ struct rsd_ctx {
     int64_t db_n = 0, db_base = 0, db_nwords = 0, db_maxlen = 0;
     int db_bits = 0;
     uint32_t db_symmask = 0;
+    bool db_loaded = false;
     DevBuf db_dist, db_topi, db_tops, db_aux;
 
     int ensure_device();
@@ -93,6 +95,9 @@ struct rsd_ctx {
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
+    int search_dev(const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len, int64_t n_queries,
+                   int64_t max_qlen, int bits, uint32_t q_symmask, int k, int force_mode, int64_t *top_idx,
+                   double *top_score, double *all_scores_dev, int *mode_out, cudaStream_t st);
     int script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t n_pairs, int bits, uint32_t symmask,
                         int force_mode, int64_t max_ops, bool with_x, uint8_t *op, int32_t *oi, int32_t *oj,
                         int32_t *n_ops, double *dist, uint8_t *ok, int *mode_out);

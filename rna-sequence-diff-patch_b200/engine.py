@@ -186,12 +186,7 @@ class Engine:
         return mode.value
 
     def topk_merge(self, idx: np.ndarray, score: np.ndarray):
-        """idx/score: [n_shards, n_queries, k] -> merged ([n_queries, k], [n_queries, k])."""
-        g, nq, k = idx.shape
-        idx = np.ascontiguousarray(idx, np.int64); score = np.ascontiguousarray(score, np.float64)
-        oi = np.zeros((nq, k), np.int64); os_ = np.zeros((nq, k), np.float64)
-        check(self._lib.rsd_topk_merge(ptr(idx, _i64), ptr(score, _f64), g, nq, k, ptr(oi, _i64), ptr(os_, _f64)))
-        return oi, os_
+        return topk_merge(idx, score)
 
     # ---- long pair ----------------------------------------------------------------------------------------
     def long_pair(self, a_codes: np.ndarray, b_codes: np.ndarray, want_script: bool = True, force_mode: int = 0):
@@ -226,6 +221,17 @@ class Engine:
     @property
     def ctx(self):
         return self._ctx
+
+
+def topk_merge(idx: np.ndarray, score: np.ndarray):
+    """idx/score: [n_shards, n_queries, k] -> merged ([n_queries, k], [n_queries, k]) with the key
+    (score descending, global index ascending) — the reduction after the NCCL gather."""
+    lib = _lib.load_library()
+    g, nq, k = idx.shape
+    idx = np.ascontiguousarray(idx, np.int64); score = np.ascontiguousarray(score, np.float64)
+    oi = np.zeros((nq, k), np.int64); os_ = np.zeros((nq, k), np.float64)
+    check(lib.rsd_topk_merge(ptr(idx, _i64), ptr(score, _f64), g, nq, k, ptr(oi, _i64), ptr(os_, _f64)))
+    return oi, os_
 
 
 _engines: dict = {}

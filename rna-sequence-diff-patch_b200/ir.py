@@ -30,10 +30,11 @@ def score_collection(query: str, sequences, costs: dict, engine=None):
     for s in sequences:                       # the reference's per-document KeyError (SED:87)
         sed._validate_and_encode(query, s, costs)
     up = [s.upper() for s in sequences]
-    db = pack(up, bits=4)
-    q = pack([query.upper()] * len(up), bits=4)
-    dist = eng.distance_batch(q, db)
-    scores = [1.0 / (1.0 + dist)]
+    eng.db_load(pack(up, bits=4))
+    try:
+        _, _, scores = eng.db_search_topk(pack([query.upper()], bits=4), k=1, want_scores=True)
+    finally:
+        eng.db_free()
     return [(s, float(v)) for s, v in zip(sequences, scores[0])]
 
 

@@ -1,0 +1,139 @@
+"""GPU parity: query batch vs database with exact top-k (score desc, index asc)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import __graft_entry__ as G
+    G.build()
+    import rna_sequence_diff_patch_b200 as R
+    assert R.load_library().rsd_device_count() > 0
+    return R
+
+
+@pytest.fixture(scope="module")
+def eng(R):
+    return R.Engine(0)
+
+
+def make_db(rng, n, lo=24, hi=31, p_n=1e-3, iupac_frac=0.0):
+    lens = rng.integers(lo, hi + 1, size=n)
+    off = np.zeros(n + 1, np.int64); np.cumsum(lens, out=off[1:])
+    codes = rng.integers(0, 4, size=int(off[-1]), dtype=np.uint8)
+    codes[rng.random(codes.shape[0]) < p_n] = 14                      # N
+    if iupac_frac > 0:
+        for r in np.nonzero(rng.random(n) < iupac_frac)[0]:
+            codes[off[r]:off[r + 1]] = rng.integers(0, 15, size=lens[r], dtype=np.uint8)
+    return codes, off
+
+
+def make_queries(rng, codes, off, nq, rate=0.1):
+    qs = []
+    for r in rng.integers(0, len(off) - 1, size=nq):
+        s = codes[off[r]:off[r + 1]].copy()
+        hit = rng.random(s.shape[0]) < rate
+        s[hit] = rng.integers(0, 4, size=int(hit.sum()), dtype=np.uint8)
+        qs.append(O.decode(s))
+    return qs
+
+
+def oracle_topk(queries, codes, off, costs, k):
+    out_i, out_s, alls = [], [], []
+    for q in queries:
+        i, s, a = O.search_topk(q, codes, off, costs, k, want_scores=True)
+        out_i.append(i); out_s.append(s); alls.append(a)
+    return np.stack(out_i), np.stack(out_s), np.stack(alls)
+
+
+def test_fast_path_acgun_topk_and_all_scores(R, eng, golden):
+    rng = np.random.default_rng(20260005)
+    codes, off = make_db(rng, 40000)
+    queries = make_queries(rng, codes, off, 6)
+    costs = golden["default_costs"]
+    eng.set_costs(costs)
+    db = R.pack((codes, off), bits=4)
+    eng.db_load(db)
+    idx, sc, alls = eng.db_search_topk(R.pack(queries, bits=4), 10, want_scores=True)
+    assert eng.last_mode == 1, "ACGU+N under default costs must take the int16x2 search kernel"
+    wi, ws, wa = oracle_topk(queries, codes, off, costs, 10)
+    assert np.array_equal(alls, wa)
+    assert np.array_equal(idx, wi) and np.array_equal(sc, ws)
+    idx2, sc2 = eng.db_search_topk(R.pack(queries, bits=4), 10, force_mode=3)      # general fp64 path agrees
+    assert np.array_equal(idx2, wi) and np.array_equal(sc2, ws)
+    eng.db_free()
+
+
+def test_ties_keep_collection_order_and_short_db(R, eng, golden):
+    base = ["ACGUACGUACGUACGUACGUACGUAC", "ACGUACGUACGUACGUACGUACGUAG", "GGGGGGGGGGGGGGGGGGGGGGGGGG"]
+    seqs = [base[k % 3] for k in range(3000)]
+    eng.set_costs(golden["default_costs"])
+    c, o = O.concat(seqs)
+    eng.db_load(R.pack(seqs, bits=4))
+    q = ["ACGUACGUACGUACGUACGUACGUAC", "GGGGGGGGGGGGGGGGGGGGGGGGGA"]
+    idx, sc = eng.db_search_topk(R.pack(q, bits=4), 25)
+    wi, ws, _ = oracle_topk(q, c, o, golden["default_costs"], 25)
+    assert np.array_equal(idx, wi) and np.array_equal(sc, ws)
+    assert idx[0].tolist() == list(range(0, 75, 3))                   # equal scores come out in collection order
+    eng.db_free()
+    eng.db_load(R.pack(seqs[:4], bits=4))
+    idx, sc = eng.db_search_topk(R.pack(q, bits=4), 10)
+    assert idx[0, :4].tolist() == [0, 3, 1, 2] and (idx[:, 4:] == -1).all()
+    eng.db_free()
+
+
+def test_iupac_records_general_fp64_path(R, eng, golden):
+    rng = np.random.default_rng(32)
+    codes, off = make_db(rng, 6000, iupac_frac=0.01)
+    queries = make_queries(rng, codes, off, 3)
+    for costs in (golden["default_costs"], golden["user_costs"]):
+        eng.set_costs(costs)
+        eng.db_load(R.pack((codes, off), bits=4))
+        idx, sc, alls = eng.db_search_topk(R.pack(queries, bits=4), 10, want_scores=True)
+        assert eng.last_mode == 3
+        wi, ws, wa = oracle_topk(queries, codes, off, costs, 10)
+        assert np.array_equal(alls, wa) and np.array_equal(idx, wi) and np.array_equal(sc, ws)
+        eng.db_free()
+
+
+def test_long_records_general_path(R, eng, golden):
+    rng = np.random.default_rng(33)
+    codes, off = make_db(rng, 3000, lo=20, hi=90, p_n=0.0)
+    queries = make_queries(rng, codes, off, 3)
+    eng.set_costs(golden["user_costs"])
+    eng.db_load(R.pack((codes, off), bits=2))
+    idx, sc = eng.db_search_topk(R.pack(queries, bits=2), 7)
+    wi, ws, _ = oracle_topk(queries, codes, off, golden["user_costs"], 7)
+    assert np.array_equal(idx, wi) and np.array_equal(sc, ws)
+    eng.db_free()
+
+
+def test_sharded_search_equals_single_shard(R, eng, golden):
+    """Ranks emulated one after another on one GPU (no co-resident ranks): shard, local top-k,
+    merge == the unsharded answer; also crosses the 32768 / 1M chunk boundaries."""
+    from rna_sequence_diff_patch_b200.dist_search import shard_bounds, slice_packed
+    from rna_sequence_diff_patch_b200.engine import topk_merge
+    rng = np.random.default_rng(34)
+    codes, off = make_db(rng, 1_100_000)
+    queries = make_queries(rng, codes, off, 2)
+    eng.set_costs(golden["default_costs"])
+    db = R.pack((codes, off), bits=4)
+    Q = R.pack(queries, bits=4)
+    eng.db_load(db)
+    gi, gs = eng.db_search_topk(Q, 10)
+    eng.db_free()
+    wi, ws, _ = oracle_topk(queries, codes, off, golden["default_costs"], 10)
+    assert np.array_equal(gi, wi) and np.array_equal(gs, ws)
+    for world in (2, 3, 8):
+        li, ls = [], []
+        for lo, hi in shard_bounds(db.len, world):
+            eng.db_load(slice_packed(db, lo, hi), global_index_base=lo)
+            i, s = eng.db_search_topk(Q, 10)
+            li.append(i); ls.append(s)
+            eng.db_free()
+        mi, ms = topk_merge(np.stack(li), np.stack(ls))
+        assert np.array_equal(mi, gi) and np.array_equal(ms, gs), world

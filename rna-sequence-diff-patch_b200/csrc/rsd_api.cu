@@ -15,6 +15,7 @@
 #include "k_ubench.cuh"
 #include "k_script.cuh"
 #include "k_search.cuh"
+#include "k_long.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -514,9 +515,6 @@ extern "C" int rsd_topk_merge(const int64_t *idx, const double *score, int n_sha
     return RSD_OK;
 }
 
-#include "rsd_stubs.cuh"
-extern "C" int rsd_long_pair(rsd_ctx *, const uint8_t *, int64_t, const uint8_t *, int64_t, int, int, int64_t,
-                             uint8_t *, int32_t *, int32_t *, int64_t *, double *, int *) { RSD_NOT_YET("rsd_long_pair"); }
 
 // ------------------------------------------------------------------------------------------------
 // edit scripts + patch (BASELINE config 3)
@@ -903,6 +901,101 @@ extern "C" int rsd_db_search_topk(rsd_ctx *c, const uint32_t *q_words, const int
         RSD_CUDA(cudaMemcpyAsync(top_score, c->s_oj.p, sizeof(double) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
     }
     if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores, c->out_f64.p, sizeof(double) * (size_t)n_queries * c->db_n, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaStreamSynchronize(st));
+    return RSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// long pair (BASELINE config 4)
+// ------------------------------------------------------------------------------------------------
+extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint8_t *b, int64_t n,
+                             int force_mode, int want_script, int64_t max_ops,
+                             uint8_t *op, int32_t *oi, int32_t *oj, int64_t *n_ops, double *dist, int *mode_out) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (m < 0 || n < 0 || (m > 0 && !a) || (n > 0 && !b) || !dist) return rsd_fail(RSD_EINVAL, "rsd_long_pair: bad arguments");
+    if (m > 0x3fffffff || n > 0x3fffffff) return rsd_fail(RSD_ERANGE, "rsd_long_pair: sequence too long");
+    if (want_script && (!op || !n_ops || max_ops < m + n)) return rsd_fail(RSD_EINVAL, "rsd_long_pair: script buffers missing or max_ops < m+n");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    uint32_t symmask = 0;
+    for (int64_t i = 0; i < m; ++i) { if (a[i] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pair: code > 15"); symmask |= 1u << a[i]; }
+    for (int64_t j = 0; j < n; ++j) { if (b[j] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pair: code > 15"); symmask |= 1u << b[j]; }
+    ModeInfo mi;
+    RSD_OK_OR_RETURN(c->classify(symmask, m, n, 4, force_mode == RSD_MODE_I16X2 ? RSD_MODE_I32 : force_mode, mi));
+    // int64 keys: cost * 2^S + steps must stay below 2^62
+    const int S = ceil_log2_i64(m + n + 66);
+    bool f64 = mi.mode == RSD_MODE_F64;
+    if (!f64) {
+        const double bound = ((double)m * mi.ic.del + (double)(n + 512) * mi.ic.ins + 4.0 * ((double)mi.ic.ins + mi.ic.del)) * std::ldexp(1.0, S);
+        if (bound > 4.0e18) { if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_long_pair: int64 key would overflow"); f64 = true; }
+    } else if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_EINVAL, "rsd_long_pair: integer mode not exact for these costs");
+    if (mode_out) *mode_out = f64 ? RSD_MODE_F64 : RSD_MODE_I32;
+    c->timed = false;
+    if (m == 0 || n == 0) {                     // border row / column only (SED:146-182): one product, all INS or all DEL
+        *dist = m == 0 ? (double)n * c->ins : (double)m * c->del;
+        if (want_script) {
+            const int64_t k = m + n;
+            for (int64_t x = 0; x < k; ++x) { op[x] = m == 0 ? 0 : 1; if (oi) oi[x] = m == 0 ? 0 : (int32_t)(x + 1); if (oj) oj[x] = m == 0 ? (int32_t)(x + 1) : 0; }
+            *n_ops = k;
+        }
+        return RSD_OK;
+    }
+    cudaStream_t st = c->stream;
+    RSD_OK_OR_RETURN(c->upload_costs(mi, st));
+    constexpr int C = 8;
+    const int n_panels = (int)((n + 32 * C - 1) / (32 * C));
+    const int64_t n_pad = (int64_t)n_panels * 32 * C;
+    int per_sm = 0;
+    if (f64) RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_long_fwd<true, C>, 32, 0));
+    else RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_long_fwd<false, C>, 32, 0));
+    if ((int64_t)per_sm * c->sm_count < n_panels)
+        return rsd_fail(RSD_ERANGE, "rsd_long_pair: %d column panels exceed the %d co-resident CTAs of this GPU (n too large for one wavefront launch)",
+                        n_panels, per_sm * c->sm_count);
+    const size_t dir_words = (size_t)((m + 15) / 16) * (size_t)n_pad;
+    RSD_OK_OR_RETURN(c->dirs.ensure(dir_words * 4 + 64));
+    RSD_OK_OR_RETURN(c->scratch.ensure((size_t)n_panels * (size_t)m * 12 + (size_t)n_panels * 4 + 256));
+    RSD_OK_OR_RETURN(c->mat_ab.ensure((size_t)m + n + 64));
+    RSD_OK_OR_RETURN(c->out_f64.ensure(64));
+    uint8_t *da = (uint8_t *)c->mat_ab.p, *db = da + ((m + 15) / 16) * 16;
+    RSD_CUDA(cudaMemcpyAsync(da, a, (size_t)m, cudaMemcpyHostToDevice, st));
+    RSD_CUDA(cudaMemcpyAsync(db, b, (size_t)n, cudaMemcpyHostToDevice, st));
+    LongArgs la{};
+    la.a = da; la.m = (int)m; la.b = db; la.n = (int)n; la.n_panels = n_panels; la.n_pad = (int)n_pad;
+    la.dirs = (uint32_t *)c->dirs.p;
+    la.bound = c->scratch.p;
+    la.bound_steps = (int *)((unsigned char *)c->scratch.p + (size_t)n_panels * (size_t)m * 8);
+    la.progress = (int *)((unsigned char *)c->scratch.p + (size_t)n_panels * (size_t)m * 12);
+    la.dist = (double *)c->out_f64.p;
+    la.S = S;
+    RSD_CUDA(cudaMemsetAsync(la.progress, 0, (size_t)n_panels * 4, st));
+    const IntCosts *dic = c->d_ic; const F64Costs *dfc = c->d_fc;
+    void *args[] = {&la, &dic, &dfc};
+    if (c->timing) RSD_CUDA(cudaEventRecord(c->ev0, st));
+    if (f64) RSD_CUDA(cudaLaunchCooperativeKernel((void *)k_long_fwd<true, C>, dim3(n_panels), dim3(32), args, 0, st));
+    else RSD_CUDA(cudaLaunchCooperativeKernel((void *)k_long_fwd<false, C>, dim3(n_panels), dim3(32), args, 0, st));
+    c->launches += 1;
+    if (want_script) {
+        RSD_OK_OR_RETURN(c->s_tmp.ensure((size_t)(m + n) + 64));
+        RSD_OK_OR_RETURN(c->s_nops.ensure(64));
+        RSD_OK_OR_RETURN(c->s_op.ensure((size_t)(m + n) + 64));
+        if (oi) RSD_OK_OR_RETURN(c->s_oi.ensure(sizeof(int32_t) * (size_t)(m + n) + 64));
+        if (oj) RSD_OK_OR_RETURN(c->s_oj.ensure(sizeof(int32_t) * (size_t)(m + n) + 64));
+        k_long_traceback<<<1, 32, 0, st>>>((int)m, (int)n, (const uint32_t *)c->dirs.p, (int)n_pad, (uint8_t *)c->s_tmp.p, (int32_t *)c->s_nops.p);
+        k_long_emit<<<1, 1024, 0, st>>>((const uint8_t *)c->s_tmp.p, (int)m, (int)n, (const int32_t *)c->s_nops.p, (uint8_t *)c->s_op.p,
+                                        oi ? (int32_t *)c->s_oi.p : nullptr, oj ? (int32_t *)c->s_oj.p : nullptr);
+        c->launches += 2;
+    }
+    if (c->timing) { RSD_CUDA(cudaEventRecord(c->ev1, st)); c->timed = true; }
+    RSD_CUDA(cudaGetLastError());
+    RSD_CUDA(cudaMemcpyAsync(dist, c->out_f64.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    int32_t k32 = 0;
+    if (want_script) {
+        RSD_CUDA(cudaMemcpyAsync(&k32, c->s_nops.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        RSD_CUDA(cudaStreamSynchronize(st));
+        *n_ops = k32;
+        RSD_CUDA(cudaMemcpyAsync(op, c->s_op.p, (size_t)k32, cudaMemcpyDeviceToHost, st));
+        if (oi) RSD_CUDA(cudaMemcpyAsync(oi, c->s_oi.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
+        if (oj) RSD_CUDA(cudaMemcpyAsync(oj, c->s_oj.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
+    }
     RSD_CUDA(cudaStreamSynchronize(st));
     return RSD_OK;
 }

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128)
 k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict__ out,
               uint32_t *__restrict__ scratch, int scratch_stride) {
     static_assert(C % 16 == 0, "strip width must be a multiple of the 2-bit word");
-    __shared__ uint32_t s_tab[4];
+    __shared__ __align__(16) uint32_t s_tab[4];
     if (threadIdx.x < 4) s_tab[threadIdx.x] = ic.rowtab4[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -75,8 +75,52 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
             for (int c = 0; c < C; ++c) H[c] = 0u;
             uint32_t last = 0u, prev_recv = 0u, curA = 0u, curB = 0u;
             const int steps = warp_max(strip_on ? m + tk.s0 : 0);
-            const bool wr_scr = tk.multi && tk.s0 == 31 && pass + 1 < npass;
 
+            if (!tk.multi) {
+                // ---- single pass (n <= 32*C): the hot loop.  Rows are consumed in blocks of 16 steps so
+                // the source codes of a block sit in one register per pair: an unaligned 16-code window
+                // (funnel shift of two packed words), rotated so the current code is at bits [3:2] and can
+                // be OR-ed into the shared-memory address of the 4-entry row table.
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_tab);
+                const int mrow = strip_on ? m : 0;
+                const bool lead = tk.s0 == 0;
+                int i = -tk.s0;
+#pragma unroll 1
+                for (int t0 = 0; t0 < steps; t0 += 16) {
+                    {
+                        const int wi = i >> 4, bit = (i & 15) * 2;            // floor division also for i < 0
+                        const int w0 = max(wi, 0), w1 = max(wi + 1, 0);
+                        const uint32_t a0 = __ldg(awA + w0), a1 = __ldg(awA + w1);
+                        const uint32_t b0 = __ldg(awB + w0), b1 = __ldg(awB + w1);
+                        curA = __funnelshift_l(__funnelshift_r(a0, a1, bit), __funnelshift_r(a0, a1, bit), 2);
+                        curB = __funnelshift_l(__funnelshift_r(b0, b1, bit), __funnelshift_r(b0, b1, bit), 2);
+                    }
+                    const int tend = min(16, steps - t0);
+#pragma unroll 1
+                    for (int k = 0; k < tend; ++k, ++i) {
+                        uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
+                        if (lead) recv = 0u;
+                        uint32_t ra, rb;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sbase | (curA & 0xCu)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sbase | (curB & 0xCu)));
+                        curA = __funnelshift_r(curA, curA, 2);
+                        curB = __funnelshift_r(curB, curB, 2);
+                        if ((unsigned)i < (unsigned)mrow) {
+                            uint32_t left = recv, diag = prev_recv;
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const uint32_t w = prmt(ra, rb, sel[c]);
+                                const uint32_t t2 = addmin16x2(diag, w, H[c]);
+                                diag = H[c];
+                                H[c] = min16x2(t2, left);
+                                left = H[c];
+                            }
+                            last = left; prev_recv = recv;
+                        }
+                    }
+                }
+            } else {
+            const bool wr_scr = tk.s0 == 31 && pass + 1 < npass;
 #pragma unroll 1
             for (int t = 0; t < steps; ++t) {
                 uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
@@ -99,6 +143,7 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                     last = left; prev_recv = recv;
                     if (wr_scr) scr[i] = last;
                 }
+            }
             }
             if (strip_on) {
                 if (s == (nA - 1) / C) {

@@ -20,13 +20,17 @@ struct SeqView {
 
 // =============================================================================================
 // Fast path: 2-bit codes (ACGU), scaled-int16 H' values, TWO pairs per register (hi/lo halves).
-// Per packed cell (= 2 matrix cells): PRMT (w lookup for both pairs, sign-extended int8 -> int16),
-// VIADDMNMX.S16x2 (min(diag + w, up)), VIMNMX.S16x2 (min(., left)).
+// Max form: N = -H' >= 0 and v = -w = ins + del - sub clamped to >= 0 (a substitution dearer than
+// delete+insert never wins, so the clamp leaves every value unchanged):
+//     N[i][j] = max(N[i][j-1], N[i-1][j], N[i-1][j-1] + v(a_i, b_j)),   D = m*del + n*ins - N.
+// Per packed cell (= 2 matrix cells): PRMT (v lookup for both pairs, alu pipe), one plain 32-bit add
+// (halves are non-negative and < 2^16, so no carry crosses; issued as IMAD on the fma pipe) and
+// VIMNMX3.U16x2 (alu pipe): 2 alu + 1 fma instructions per two cells.
 // =============================================================================================
 template <int C>
 __global__ void __launch_bounds__(128)
 k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict__ out,
-              uint32_t *__restrict__ scratch, int scratch_stride) {
+              uint32_t *__restrict__ scratch, int scratch_stride, uint32_t one) {
     static_assert(C % 16 == 0, "strip width must be a multiple of the 2-bit word");
     __shared__ __align__(16) uint32_t s_tab[4];
     if (threadIdx.x < 4) s_tab[threadIdx.x] = ic.rowtab4[threadIdx.x];
@@ -109,10 +113,10 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                             uint32_t left = recv, diag = prev_recv;
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
-                                const uint32_t w = prmt(ra, rb, sel[c]);
-                                const uint32_t t2 = addmin16x2(diag, w, H[c]);
+                                const uint32_t v = prmt(ra, rb, sel[c]);
+                                const uint32_t x = add_fma(v, diag, one);
                                 diag = H[c];
-                                H[c] = min16x2(t2, left);
+                                H[c] = max3u16x2(x, H[c], left);
                                 left = H[c];
                             }
                             last = left; prev_recv = recv;
@@ -134,10 +138,10 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                     uint32_t left = recv, diag = prev_recv;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const uint32_t w = prmt(ra, rb, sel[c]);
-                        const uint32_t t2 = addmin16x2(diag, w, H[c]);
+                        const uint32_t v = prmt(ra, rb, sel[c]);
+                        const uint32_t x = add_fma(v, diag, one);
                         diag = H[c];
-                        H[c] = min16x2(t2, left);
+                        H[c] = max3u16x2(x, H[c], left);
                         left = H[c];
                     }
                     last = left; prev_recv = recv;
@@ -151,14 +155,14 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    resA = (int)(int16_t)(v & 0xffffu);
+                    resA = (int)(v & 0xffffu);
                 }
                 if (s == (nB - 1) / C) {
                     const int cl = (nB - 1) - s * C;
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    resB = (int)(int16_t)(v >> 16);
+                    resB = (int)(v >> 16);
                 }
             }
             __syncwarp();
@@ -166,10 +170,10 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
         if (tk.on) {
             const int sA = tk.multi ? ((nA - 1) / C) & 31 : (nA - 1) / C;
             if (tk.s0 == sA)
-                out[tk.pA] = (double)(resA + m * ic.del + nA * ic.ins) * inv_scale;
+                out[tk.pA] = (double)(m * ic.del + nA * ic.ins - resA) * inv_scale;
             const int sB = tk.multi ? ((nB - 1) / C) & 31 : (nB - 1) / C;
             if (tk.hasB && tk.s0 == sB)
-                out[tk.pB] = (double)(resB + m * ic.del + nB * ic.ins) * inv_scale;
+                out[tk.pB] = (double)(m * ic.del + nB * ic.ins - resB) * inv_scale;
         }
     }
 }

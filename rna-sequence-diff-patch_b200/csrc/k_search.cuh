@@ -4,12 +4,13 @@
 // document, IR:435-440) and the stable descending sort + [:k] of performance.py:12-15.
 //
 // Fast kernel (records <= 32 symbols, <= 7 distinct symbols incl. the queries', dyadic costs):
-//   one thread = two database records (lo / hi half of every register, int16 H' values), the
-//   record right-aligned in 32 column registers and left-padded with a PAD symbol whose w >= 0
-//   keeps H' at the border value 0 — so the answer is always in column register 31.
+//   one thread = two database records (lo / hi half of every register, uint16 N = -H' values, max
+//   form as in k_dist_twin16), the record right-aligned in 32 column registers and left-padded with
+//   a PAD symbol whose v = 0 keeps N at the border value 0 — so the answer is always in column
+//   register 31.
 //   The query symbol of a row is uniform over the whole grid: its 8-byte row of the compact cost
 //   table comes from shared memory with one broadcast LDS.64, and each packed cell is
-//   PRMT (both records' w, sign-extended) + VIADDMNMX.S16x2 + VIMNMX.S16x2.
+//   PRMT (both records' v) + IMAD (packed add, fma pipe) + VIMNMX3.U16x2.
 //   The record's selector registers are built once and reused for every query of the batch.
 // Top-k: a candidate passes when its key (score desc, global index asc) is not worse than the
 //   current k-th best key of its query (tau).  tau starts at "accept all" and is tightened after
@@ -35,12 +36,12 @@ struct TopkState {
     int k;
 };
 
-// rowtab[q][i] = 8 bytes: (int8) w(query symbol i of q, compact symbol 0..7); byte 7 (PAD) = +127
+// rowtab[q][i] = 8 bytes: v(query symbol i of q, compact symbol 0..6) = max(0, -w) <= 127; byte 7 (PAD) = 0
 __global__ void __launch_bounds__(128)
 k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_start,
                 const int32_t *__restrict__ db_len, int64_t rec0, int64_t n_rec, int db_bits, int64_t global_base,
                 const uint2 *__restrict__ rowtab, int QROWS, const int32_t *__restrict__ q_len, int n_queries,
-                SearchTab tab, TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
+                SearchTab tab, TopkState tk, double *__restrict__ all_scores, int64_t all_stride, uint32_t one) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2 *s_rows = reinterpret_cast<uint2 *>(smem_raw);                     // [n_queries][QROWS]
     double *s_tau = reinterpret_cast<double *>(s_rows + (size_t)n_queries * QROWS);
@@ -97,15 +98,15 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
             uint32_t left = 0u, diag = 0u;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                const uint32_t w = prmt(r.x, r.y, sel[c]);
-                const uint32_t t2 = addmin16x2(diag, w, H[c]);
+                const uint32_t v = prmt(r.x, r.y, sel[c]);
+                const uint32_t x = add_fma(v, diag, one);
                 diag = H[c];
-                H[c] = min16x2(t2, left);
+                H[c] = max3u16x2(x, H[c], left);
                 left = H[c];
             }
         }
-        const int dA = (int)(int16_t)(H[31] & 0xffffu) + m * tab.del + baseA;
-        const int dB = (int)(int16_t)(H[31] >> 16) + m * tab.del + baseB;
+        const int dA = m * tab.del + baseA - (int)(H[31] & 0xffffu);
+        const int dB = m * tab.del + baseB - (int)(H[31] >> 16);
         // IR:440  score = 1 / (1 + cost)
         const double sA = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dA, tab.inv_scale)));
         const double sB = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dB, tab.inv_scale)));
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) k_topk_fold(TopkState tk) {
 }
 
 
-// rowtab[q][i] from the packed queries: byte b < 7 = (int8) w(query symbol, compact symbol b), byte 7 = +127 (PAD)
+// rowtab[q][i] from the packed queries: byte b < 7 = v(query symbol, compact symbol b), byte 7 = 0 (PAD)
 __global__ void k_build_rowtab(const uint32_t *__restrict__ q_words, const int64_t *__restrict__ q_start,
                                const int32_t *__restrict__ q_len, int n_queries, int bits, int QROWS,
                                const IntCosts *__restrict__ ic, uint32_t compact_syms_lo, uint32_t compact_syms_hi,
@@ -228,16 +229,15 @@ __global__ void k_build_rowtab(const uint32_t *__restrict__ q_words, const int64
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_queries * QROWS) return;
     const int q = idx / QROWS, i = idx % QROWS;
-    uint2 r = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+    uint2 r = make_uint2(0u, 0u);
     if (i < q_len[q]) {
         const uint32_t a = pk_get(q_words, q_start[q], i, bits);
         const uint64_t syms = ((uint64_t)compact_syms_hi << 32) | compact_syms_lo;   // 7 x 4-bit original codes
         uint64_t v = 0;
         for (int b = 0; b < 7; ++b) {
             const uint32_t sym = (uint32_t)(syms >> (4 * b)) & 15u;
-            v |= (uint64_t)(uint8_t)(int8_t)ic->w[a][sym] << (8 * b);
+            v |= (uint64_t)(uint8_t)max(0, -ic->w[a][sym]) << (8 * b);
         }
-        v |= (uint64_t)0x7f << 56;
         r = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
     }
     rowtab[idx] = r;

@@ -167,19 +167,19 @@ int rsd_ctx::classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, 
                     w = (int64_t)std::ldexp(sub[a][b], k) - ic.ins - ic.del;
                 else w = 0;                                   // unreachable entry
                 if (std::llabs(w) > maxabsw) maxabsw = std::llabs(w);
-                if (a < 4 && b < 4 && (w < -128 || w > 127)) w8 = false;
+                if (a < 4 && b < 4 && (w < -127)) w8 = false;            // v = max(0, -w) must fit a non-negative int8
                 ic.w[a][b] = (int32_t)std::max<int64_t>(std::min<int64_t>(w, INT32_MAX), INT32_MIN);
             }
         // |H'| <= i*del + j*ins on the extended (strip-padded) matrix
         const int64_t pad_n = max_n + 64;
         const double bound = (double)max_m * ic.del + (double)pad_n * ic.ins + (double)maxabsw;
         i32_ok = bound < 2147483000.0;
-        i16_ok = bound < 32760.0;
+        i16_ok = bound < 65000.0;                                 // unsigned 16-bit N = -H'
         fast_ok = i16_ok && w8 && bits == 2 && (symmask & ~0xFu) == 0;
         if (fast_ok)
             for (int a = 0; a < 4; ++a) {
                 uint32_t r = 0;
-                for (int b = 0; b < 4; ++b) r |= (uint32_t)(uint8_t)(int8_t)ic.w[a][b] << (8 * b);
+                for (int b = 0; b < 4; ++b) r |= (uint32_t)std::max(0, -ic.w[a][b]) << (8 * b);
                 ic.rowtab4[a] = r;
             }
     }
@@ -327,7 +327,7 @@ int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const
         const int stride = max_n > 32 * C ? (int)max_m : 0;
         RSD_OK_OR_RETURN(scratch.ensure(sizeof(uint32_t) * (size_t)stride * blocks * wpb + 16));
         if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
-        k_dist_twin16<C><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)scratch.p, stride);
+        k_dist_twin16<C><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)scratch.p, stride, 1u);
     } else if (mi.mode == RSD_MODE_I32) {
         constexpr int C = 32;
         RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv));
@@ -786,7 +786,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     }
     if (mi.dyadic)
         for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b)
-            if ((symmask >> a & 1) && (symmask >> b & 1) && (mi.ic.w[a][b] < -128 || mi.ic.w[a][b] > 126)) w8 = false;
+            if ((symmask >> a & 1) && (symmask >> b & 1) && mi.ic.w[a][b] < -127) w8 = false;
     const int QROWS = (int)((max_qlen + 7) / 8 * 8);
     const bool fast = mi.dyadic && mi.i16_ok && w8 && nsym <= 7 && db_maxlen <= 32 && max_qlen >= 1 && QROWS <= 64 &&
                       (force_mode == 0 || force_mode == RSD_MODE_I16X2);
@@ -836,7 +836,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
                 const int64_t threads = (nr + 1) / 2;
                 const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
                 k_search_twin16<<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, db_base, rowtab, QROWS,
-                                                                                      q_len + q0, nq, tab, tk, alls, db_n);
+                                                                                      q_len + q0, nq, tab, tk, alls, db_n, 1u);
                 launches += 1;
             } else {
                 for (int q = 0; q < nq; ++q) {

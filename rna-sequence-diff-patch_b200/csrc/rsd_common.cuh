@@ -17,7 +17,7 @@ struct IntCosts {
     int32_t ins, del;        // scaled by 2^k
     int32_t w[16][16];       // w[a][b] = sub(a,b) - ins - del (scaled); w[a][a] = -(ins+del)
     int32_t scale_log2;      // k
-    uint32_t rowtab4[4];     // 2-bit fast path: byte b of rowtab4[a] = (int8) w[a][b]
+    uint32_t rowtab4[4];     // 2-bit fast path: byte b of rowtab4[a] = v[a][b] = max(0, -w[a][b]) (<= 127)
 };
 struct F64Costs {
     double ins, del;
@@ -45,6 +45,14 @@ __device__ __forceinline__ uint32_t addmin16x2(uint32_t a, uint32_t b, uint32_t 
 __device__ __forceinline__ uint32_t min16x2(uint32_t a, uint32_t b) {
     return __vimin3_s16x2(a, b, b);
 }
+// packed add on the fma pipe: a * one + b with `one` an opaque kernel argument equal to 1, so ptxas
+// keeps an IMAD instead of folding it into an alu-pipe IADD3.  Halves must not carry into each other.
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t max3u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ int addmin32(int a, int b, int c) { return __viaddmin_s32(a, b, c); }
 
 __device__ __forceinline__ int warp_max(int v) {

@@ -203,7 +203,7 @@ def main():
         _lib.check(lib.rsd_distance_batch(
             eng.ctx, cptr(hp["aw"], C.c_uint32), cptr(hp["as_"], C.c_int64), cptr(hp["al"], C.c_int32), A.words.shape[0],
             cptr(hp["bw"], C.c_uint32), cptr(hp["bs"], C.c_int64), cptr(hp["bl"], C.c_int32), B.words.shape[0],
-            args.pairs, A.bits, symmask, 0, cptr(out_host, C.c_double), C.byref(mode)))
+            args.pairs, max_m, max_n, A.bits, symmask, 0, cptr(out_host, C.c_double), C.byref(mode)))
 
     def barrier():
         if world > 1:

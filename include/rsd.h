@@ -94,12 +94,15 @@ int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int bits,
 
 /* ---- batched distance: replaces wagnerFisher(...)[-1][-1].value (SED:133-224, IR:439) -------
  * pair p = (source sequence p of A, destination sequence p of B); out[p] = D[m][n] as fp64.
+ * max_m / max_n: upper bounds of the source / destination lengths as recorded at pack time
+ * (0 = let the library scan a_len / b_len; an understated bound is an error the library cannot see).
  * force_mode: 0 = classify, or one of RSD_MODE_* (tests use it to cross-check the modes; forcing
- * an INT mode on costs that are not exactly representable fails with RSD_EINVAL). */
+ * an INT mode on costs that are not exactly representable fails with RSD_EINVAL).
+ * Large batches are copied in three chunks on a copy stream while earlier chunks compute. */
 int rsd_distance_batch(rsd_ctx *ctx,
                        const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
                        const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
-                       int64_t n_pairs, int bits, uint32_t symmask, int force_mode,
+                       int64_t n_pairs, int64_t max_m, int64_t max_n, int bits, uint32_t symmask, int force_mode,
                        double *out, int *mode_out);
 /* same, all pointers are device pointers, asynchronous on `stream` (a cudaStream_t) */
 int rsd_distance_batch_dev(rsd_ctx *ctx,

@@ -4,13 +4,14 @@
 // owned by warp w (one warp per CTA so panels spread over all SMs) and, inside the panel, lane s
 // owns C columns in registers — the same systolic row pipeline as the batched kernels.  Panels run
 // concurrently as a second-level pipeline: the right-most column of panel w streams through a
-// global boundary array to panel w+1, which follows ~48 rows behind (progress counter with
-// release/acquire fences).  All CTAs are co-resident (cooperative launch), so the waits cannot
+// global boundary array to panel w+1, which follows ~48 rows behind (each boundary cell is its own
+// ready flag: the array is preset to a sentinel and polled).  All CTAs are co-resident (cooperative launch), so the waits cannot
 // deadlock.  Directions are 2 bit/cell, accumulated 16 rows per register and written with 128-bit
 // stores; the traceback walks them from (m,n).
 //
-// Keys are (cost, steps) folded into one int64 (cost << S | steps) in the H' form of k_script.cuh
-// — int32 would overflow at 50 kb — or (fp64 cost, int steps) when the costs are not dyadic.
+// Keys are (cost, steps) folded into one integer (cost << S | steps) in the H' form of k_script.cuh,
+// held exactly in a double (int32 would overflow at 50 kb; see k_long_fwd) — or (fp64 cost, int
+// steps) when the costs are not dyadic.
 // Replaces (reference): wagnerFisher + create_paths(dp)[0] + generate_es for a pair the reference
 // cannot hold in memory (~500 B per cell).
 #pragma once
@@ -26,16 +27,40 @@ struct LongArgs {
     int *progress;                     // [n_panels] rows published
     double *dist;
     int S;
+    unsigned long long *dbg;           // optional [n_panels][4]: start ns, end ns, poll clocks, publish clocks
 };
 
+// boundary cells are their own "ready" flag: the array is preset to this bit pattern (memset 0x80,
+// as a double a tiny negative number) which no key (an integer) and no cost (>= 0) can take, and a
+// consumer polls until it changes — no fences on the integer path.
+#define RSD_LONG_SENTINEL 0x8080808080808080ull
+
+// polling must be a strong access: ptxas may (and does) collapse a loop of weak loads into one load.
+// gpu scope is enough (producer and consumer are CTAs of one grid) and, unlike a volatile (= sys
+// scope) load, it leaves this SM's L1 contents alone.
+__device__ __forceinline__ unsigned long long ld_poll_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Values are doubles in both modes.  Integer (dyadic-cost) mode stores the int (cost<<S | steps) key
+// of k_script.cuh *as a double*: |key| < 2^52, so every add is exact and DADD / DMNMX / DSETP act as a
+// 53-bit integer ALU on the fp64 pipe (full rate on B200) — one instruction per min instead of the
+// four a 64-bit integer min costs.  F64 mode keeps (fp64 cost, int steps) like k_script_fwd<true>.
 template <bool F64, int C>
 __global__ void __launch_bounds__(32)
 k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__restrict__ fcp) {
-    using T = typename std::conditional<F64, double, long long>::type;
-    __shared__ T s_w[256];
+    __shared__ double s_w[256];
+    __shared__ double s_pub[16];
+    __shared__ int s_pub_s[16];
+    __shared__ uint8_t s_a[64];                    // source symbols of rows t0-31 .. t0+15 of the current block
     for (int k = threadIdx.x; k < 256; k += 32) {
         if constexpr (F64) s_w[k] = fcp->sub[k >> 4][k & 15];
-        else s_w[k] = ((long long)icp->w[k >> 4][k & 15] << la.S) - 1;            // (w << S) - 1
+        else s_w[k] = (double)(((long long)icp->w[k >> 4][k & 15] << la.S) - 1);   // (w << S) - 1, exact
     }
     __syncwarp();
     const int lane = threadIdx.x;
@@ -43,132 +68,190 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
     const int m = la.m, n = la.n;
     const int col0 = (w * 32 + lane) * C;
     const bool strip_on = col0 < n;
-    T c_ins = 0, c_del = 0;
+    double c_ins = 0, c_del = 0;
     if constexpr (F64) { c_ins = fcp->ins; c_del = fcp->del; }
 
     int bc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) bc[c] = (col0 + c < n) ? la.b[col0 + c] : 0;
-    T H[C]; int HS[F64 ? C : 1]; uint32_t acc[C];
+    double H[C]; int HS[F64 ? C : 1]; uint32_t acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         acc[c] = 0u;
         if constexpr (F64) { H[c] = __dmul_rn((double)(col0 + c + 1), c_ins); HS[c] = col0 + c + 1; }
-        else H[c] = 0;
+        else H[c] = 0.0;
     }
-    T last = 0, prev_recv = 0; int last_s = 0, prev_recv_s = 0;
-    T *bin = w > 0 ? (T *)la.bound + (size_t)(w - 1) * m : nullptr;
-    T *bout = (T *)la.bound + (size_t)w * m;
-    int *bin_s = (F64 && w > 0) ? la.bound_steps + (size_t)(w - 1) * m : nullptr;
+    double last = 0, prev_recv = 0; int last_s = 0, prev_recv_s = 0;
+    const unsigned long long *bin = w > 0 ? (const unsigned long long *)la.bound + (size_t)(w - 1) * m : nullptr;
+    unsigned long long *bout = (unsigned long long *)la.bound + (size_t)w * m;
+    const volatile int *bin_s = (F64 && w > 0) ? la.bound_steps + (size_t)(w - 1) * m : nullptr;
     int *bout_s = F64 ? la.bound_steps + (size_t)w * m : nullptr;
-    volatile int *prog_in = w > 0 ? la.progress + (w - 1) : nullptr;
     const bool publish = (w + 1 < la.n_panels);
     uint32_t *dcol = la.dirs + col0;
-    const int steps = m + 31;
-    int avail = w > 0 ? 0 : m;                      // rows of the left boundary known to be published
+    const int steps = m + 31 + 16;                  // + one block so the last rows get published
+    unsigned long long dbg_t0 = 0, dbg_poll = 0, dbg_pub = 0, dbg_ld = 0, dbg_loop = 0;
+    if (la.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
 #pragma unroll 1
-    for (int t = 0; t < steps; ++t) {
-        // lane 0 consumes boundary row t: make sure the producer panel has published it
-        if (w > 0 && t < m && t >= avail) {
+    for (int t0 = 0; t0 < steps; t0 += 16) {
+        // (0) rows finished by lane 31 during the previous block (t0-16-31 .. t0-1-31) go to the next panel:
+        //     16 lanes, one coalesced non-blocking store each
+        long long c0 = la.dbg ? clock64() : 0;
+        if (publish && lane < 16) {
+            const int r = t0 - 47 + lane;
+            if (r >= 0 && r < m) {
+                if constexpr (F64) { bout_s[r] = s_pub_s[lane]; __threadfence(); }
+                st_cg_u64(bout + r, (unsigned long long)__double_as_longlong(s_pub[lane]));
+            }
+        }
+        __syncwarp();
+        if (la.dbg) { long long c1 = clock64(); dbg_pub += (unsigned long long)(c1 - c0); c0 = c1; }
+        // (1) the 16 boundary cells lane 0 will consume in this block, fetched by lanes 0..15 in parallel
+        //     The loop condition is a warp vote so all 32 lanes leave it together: a per-lane spin would
+        //     leave the warp split in two for the rest of the block (every instruction issued twice).
+        double bval = 0; int bval_s = 0;
+        if (w > 0) {
+            const bool mine = lane < 16 && t0 + lane < m;
+            unsigned long long raw = 0ull;
+            do {
+                if (mine) raw = ld_poll_u64(bin + t0 + lane);
+            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));
+            if (mine) {
+                bval = __longlong_as_double((long long)raw);
+                if constexpr (F64) bval_s = bin_s[t0 + lane];
+            }
+        }
+        if (la.dbg) { __syncwarp(); long long c1 = clock64(); dbg_poll += (unsigned long long)(c1 - c0); c0 = c1; }
+        // (2) this lane's 16 source symbols (rows t0-lane .. t0-lane+15), 4 bits each
+        //     staged through shared memory: two coalesced byte loads per lane per block
+        unsigned long long codes = 0ull;
+        {
+            const int r0 = t0 - 31 + lane, r1 = t0 + 1 + lane;
+            s_a[lane] = ((unsigned)r0 < (unsigned)m) ? la.a[r0] : (uint8_t)0;
+            if (lane < 15) s_a[32 + lane] = ((unsigned)r1 < (unsigned)m) ? la.a[r1] : (uint8_t)0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) codes |= (unsigned long long)s_a[31 - lane + k] << (4 * k);
+            __syncwarp();
+        }
+        if (la.dbg) { __syncwarp(); long long c1 = clock64(); dbg_ld += (unsigned long long)(c1 - c0 + (codes & 0)); c0 = c1; }
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const int t = t0 + k;
+            double recv = __shfl_up_sync(RSD_FULL, last, 1);
+            int recv_s = 0;
+            if constexpr (F64) recv_s = __shfl_up_sync(RSD_FULL, last_s, 1);
+            const double b0 = __shfl_sync(RSD_FULL, bval, k);
+            int b0_s = 0;
+            if constexpr (F64) b0_s = __shfl_sync(RSD_FULL, bval_s, k);
+            const int i = t - lane;
+            const bool row_on = strip_on && (unsigned)i < (unsigned)m;
             if (lane == 0) {
-                int p;
-                do { p = *prog_in; } while (p <= t);
-                avail = p;
+                if (w > 0) { recv = b0; recv_s = b0_s; }
+                else if constexpr (F64) { recv = __dmul_rn((double)(i + 1), c_del); recv_s = i + 1; }
+                else recv = 0.0;
             }
-            avail = __shfl_sync(RSD_FULL, avail, 0);
-            __threadfence();
-        }
-        T recv = __shfl_up_sync(RSD_FULL, last, 1);
-        int recv_s = 0;
-        if constexpr (F64) recv_s = __shfl_up_sync(RSD_FULL, last_s, 1);
-        const int i = t - lane;
-        const bool row_on = strip_on && (unsigned)i < (unsigned)m;
-        if (lane == 0) {
-            if (w > 0) {
-                if (row_on) { recv = __ldcg(bin + i); if constexpr (F64) recv_s = __ldcg(bin_s + i); }
-            } else if constexpr (F64) { recv = __dmul_rn((double)(i + 1), c_del); recv_s = i + 1; }
-            else recv = 0;
-        }
-        if (row_on) {
-            const int rowbase = (int)la.a[i] << 4;
-            T left = recv, diag = prev_recv; int left_s = recv_s, diag_s = prev_recv_s;
-            if constexpr (F64) {
-                if (i == 0) { diag = (col0 == 0) ? 0.0 : __dmul_rn((double)col0, c_ins); diag_s = col0; }
-                else if (col0 == 0) { diag = __dmul_rn((double)i, c_del); diag_s = i; }
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const T wv = s_w[rowbase + bc[c]];
-                uint32_t code;
+            const int rowbase = (int)((codes >> (4 * k)) & 15ull) << 4;
+            if (row_on) {
+                double left = recv, diag = prev_recv; int left_s = recv_s, diag_s = prev_recv_s;
                 if constexpr (F64) {
-                    const double c0 = __dadd_rn(left, c_ins), c1 = __dadd_rn(H[c], c_del), c2 = __dadd_rn(diag, wv);
-                    const int s0 = left_s + 1, s1 = HS[c] + 1, s2 = diag_s + 1;
-                    const double v = fmin(fmin(c0, c1), c2);
-                    int bs = (c0 == v) ? s0 : 0x7fffffff; code = 0u;
-                    if (c1 == v && s1 < bs) { bs = s1; code = 1u; }
-                    if (c2 == v && s2 < bs) { bs = s2; code = 2u; }
-                    diag = H[c]; diag_s = HS[c]; H[c] = v; HS[c] = bs; left = v; left_s = bs;
-                } else {
-                    const long long x = diag + wv;
-                    const bool p_del = H[c] <= x;                 // DEL before UPD
-                    const long long t2 = p_del ? H[c] : x;
-                    const bool p_ins = left <= t2;                // INS first
-                    diag = H[c];
-                    H[c] = p_ins ? left : t2;
-                    left = H[c];
-                    code = p_ins ? 0u : (p_del ? 1u : 2u);
+                    if (i == 0) { diag = (col0 == 0) ? 0.0 : __dmul_rn((double)col0, c_ins); diag_s = col0; }
+                    else if (col0 == 0) { diag = __dmul_rn((double)i, c_del); diag_s = i; }
                 }
-                acc[c] = __funnelshift_r(acc[c], code, 2);
-            }
-            last = left; prev_recv = recv;
-            if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
-            if ((i & 15) == 15 || i == m - 1) {
-                const int sh = 2 * (15 - (i & 15));
-                uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
 #pragma unroll
-                for (int c = 0; c < C; c += 4)
-                    dst[c >> 2] = make_uint4(acc[c] >> sh, acc[c + 1] >> sh, acc[c + 2] >> sh, acc[c + 3] >> sh);
+                for (int c = 0; c < C; ++c) {
+                    const double wv = s_w[rowbase + bc[c]];
+                    uint32_t code;
+                    if constexpr (F64) {
+                        const double c0 = __dadd_rn(left, c_ins), c1 = __dadd_rn(H[c], c_del), c2 = __dadd_rn(diag, wv);
+                        const int s0 = left_s + 1, s1 = HS[c] + 1, s2 = diag_s + 1;
+                        const double v = fmin(fmin(c0, c1), c2);
+                        int bs = (c0 == v) ? s0 : 0x7fffffff; code = 0u;
+                        if (c1 == v && s1 < bs) { bs = s1; code = 1u; }
+                        if (c2 == v && s2 < bs) { bs = s2; code = 2u; }
+                        diag = H[c]; diag_s = HS[c]; H[c] = v; HS[c] = bs; left = v; left_s = bs;
+                    } else {
+                        const double x = __dadd_rn(diag, wv);
+                        const bool p_del = H[c] <= x;                 // DEL before UPD
+                        const double t2 = p_del ? H[c] : x;           // (no NaNs here: select == fmin, one DSETP)
+                        const bool p_ins = left <= t2;                // INS first
+                        diag = H[c];
+                        H[c] = p_ins ? left : t2;
+                        left = H[c];
+                        code = p_ins ? 0u : (p_del ? 1u : 2u);
+                    }
+                    acc[c] = __funnelshift_r(acc[c], code, 2);
+                }
+                last = left; prev_recv = recv;
+                if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
+                if ((i & 15) == 15 || i == m - 1) {
+                    const int sh = 2 * (15 - (i & 15));
+                    uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
+#pragma unroll
+                    for (int c = 0; c < C; c += 4)
+                        dst[c >> 2] = make_uint4(acc[c] >> sh, acc[c + 1] >> sh, acc[c + 2] >> sh, acc[c + 3] >> sh);
+                }
             }
+            // lane 31 owns the panel's right-most column (row t-31 at this step): park it for the block-end store
+            if (lane == 31) { s_pub[k] = last; if constexpr (F64) s_pub_s[k] = last_s; }
         }
-        // lane 31 finished row i31 = t - 31: publish it for the next panel, 16 rows at a time
-        if (publish && lane == 31) {
-            const int i31 = t - 31;
-            if (i31 >= 0 && i31 < m) {
-                bout[i31] = last; if constexpr (F64) bout_s[i31] = last_s;
-                if ((i31 & 15) == 15 || i31 == m - 1) { __threadfence(); *(volatile int *)(la.progress + w) = i31 + 1; }
-            }
-        }
+        __syncwarp();
+        if (la.dbg) dbg_loop += (unsigned long long)(clock64() - c0);
+    }
+    if (la.dbg && lane == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        la.dbg[w * 8 + 0] = dbg_t0; la.dbg[w * 8 + 1] = t1; la.dbg[w * 8 + 2] = dbg_poll; la.dbg[w * 8 + 3] = dbg_pub; la.dbg[w * 8 + 4] = dbg_ld; la.dbg[w * 8 + 5] = dbg_loop;
     }
     // the cell (m, n) lives in panel (n-1)/(32C), lane ((n-1)/C)%32, column (n-1)%C
     if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
         const int cl = (n - 1) - col0;
-        T res = 0;
+        double res = 0;
 #pragma unroll
         for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
         if constexpr (F64) la.dist[0] = res;
         else {
-            const long long key = res + (long long)m * (((long long)icp->del << la.S) + 1) + (long long)n * (((long long)icp->ins << la.S) + 1);
+            const long long key = (long long)res + (long long)m * (((long long)icp->del << la.S) + 1) + (long long)n * (((long long)icp->ins << la.S) + 1);
             la.dist[0] = (double)(key >> la.S) / (double)(1 << icp->scale_log2);
         }
     }
 }
 
-// one thread: walk the direction words; ops written sink->origin from the end of tmp[0 .. m+n)
-__global__ void k_long_traceback(int m, int n, const uint32_t *__restrict__ dirs, int n_pad,
-                                 uint8_t *__restrict__ tmp, int32_t *__restrict__ n_ops) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int64_t pos = (int64_t)m + n;
+// Traceback of the long pair: one warp.  The walk is a chain of ~m+n dependent reads, so the warp
+// stages a 64-row x 64-column tile of direction words around the current cell in shared memory with
+// coalesced loads, lane 0 walks inside the tile (shared-memory latency per step instead of an HBM
+// miss), and the warp reloads when the path leaves the tile.  Ops are written sink->origin from the
+// end of tmp[0 .. m+n).
+__global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint32_t *__restrict__ dirs, int n_pad,
+                                                       uint8_t *__restrict__ tmp, int32_t *__restrict__ n_ops) {
+    constexpr int TR = 4, TC = 64;                 // row blocks (16 rows each) x columns per tile
+    __shared__ uint32_t tile[TR][TC];
+    const int lane = threadIdx.x;
     int i = m, j = n;
+    int pos = m + n;
     while (i > 0 && j > 0) {
-        const uint32_t wv = dirs[(size_t)((i - 1) >> 4) * n_pad + (j - 1)];
-        const uint32_t code = (wv >> (2 * ((i - 1) & 15))) & 3u;
-        tmp[--pos] = (uint8_t)code;
-        if (code == 0u) --j; else if (code == 1u) --i; else { --i; --j; }
+        const int rb_hi = (i - 1) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
+        const int c_hi = j - 1, c_lo = max(c_hi - TC + 1, 0);
+        const int nr = rb_hi - rb_lo + 1, nc = c_hi - c_lo + 1;
+        for (int r = 0; r < nr; ++r)
+            for (int c = lane; c < nc; c += 32) tile[r][c] = dirs[(size_t)(rb_lo + r) * n_pad + c_lo + c];
+        __syncwarp();
+        if (lane == 0) {
+            const int i_min = rb_lo * 16;
+            while (i > i_min && j > c_lo) {
+                const uint32_t wv = tile[((i - 1) >> 4) - rb_lo][(j - 1) - c_lo];
+                const uint32_t code = (wv >> (2 * ((i - 1) & 15))) & 3u;
+                tmp[--pos] = (uint8_t)code;
+                if (code == 0u) --j; else if (code == 1u) --i; else { --i; --j; }
+            }
+        }
+        i = __shfl_sync(RSD_FULL, i, 0); j = __shfl_sync(RSD_FULL, j, 0); pos = __shfl_sync(RSD_FULL, pos, 0);
+        __syncwarp();
     }
-    while (j > 0) { tmp[--pos] = 0; --j; }
-    while (i > 0) { tmp[--pos] = 1; --i; }
-    n_ops[0] = (int32_t)((int64_t)m + n - pos);
+    if (lane == 0) {
+        while (j > 0) { tmp[--pos] = 0; --j; }
+        while (i > 0) { tmp[--pos] = 1; --i; }
+        n_ops[0] = m + n - pos;
+    }
 }
 
 // packed script of the single pair: op + entered cell via two block scans (same as k_finalize, unpacked input)

@@ -6,9 +6,11 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <chrono>
 
 #include "k_dist.cuh"
 #include "k_matrix.cuh"
@@ -70,8 +72,14 @@ int rsd_ctx::ensure_device() {
                         prop.major, prop.minor);
     sm_count = prop.multiProcessorCount;
     RSD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    RSD_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RSD_CUDA(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
+    for (int k = 0; k < RSD_MAX_CHUNKS; ++k) RSD_CUDA(cudaEventCreate(&ev_chunk[k]));
+    RSD_CUDA(cudaEventCreate(&ev_begin));
     RSD_CUDA(cudaEventCreate(&ev0));
     RSD_CUDA(cudaEventCreate(&ev1));
+    cur_ev0 = ev0; cur_ev1 = ev1;
+    for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { RSD_CUDA(cudaEventCreate(&ev_t0[k])); RSD_CUDA(cudaEventCreate(&ev_t1[k])); }
     RSD_CUDA(cudaMalloc(&d_ic, sizeof(IntCosts)));
     RSD_CUDA(cudaMalloc(&d_fc, sizeof(F64Costs)));
     pid = getpid();
@@ -87,7 +95,9 @@ extern "C" int rsd_destroy(rsd_ctx *c) {
         c->free_all();
         cudaFree(c->d_ic); cudaFree(c->d_fc);
         cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-        cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+        cudaEventDestroy(c->ev_sync);
+        for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { cudaEventDestroy(c->ev_chunk[k]); cudaEventDestroy(c->ev_t0[k]); cudaEventDestroy(c->ev_t1[k]); }
     }
     delete c;
     return RSD_OK;
@@ -107,6 +117,7 @@ extern "C" int rsd_host_free(void *p) {
 extern "C" int64_t rsd_launch_count(rsd_ctx *c) { return c ? c->launches : 0; }
 extern "C" int rsd_set_timing(rsd_ctx *c, int on) { if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL"); c->timing = on != 0; return RSD_OK; }
 extern "C" double rsd_last_kernel_ms(rsd_ctx *c) {
+    if (c && c->last_ms_override > 0.0) return c->last_ms_override;
     if (!c || !c->inited || !c->timed) return 0.0;
     float ms = 0.f;
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.0;
@@ -264,22 +275,30 @@ extern "C" int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int
 // planning
 // ------------------------------------------------------------------------------------------------
 int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin,
-                       double *d_out, cudaStream_t st, PlanView &pv) {
+                       double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m) {
     RSD_OK_OR_RETURN(plan_pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * (size_t)(4 * (RSD_NB + 1) + 8)));
+    RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8)));
+    pv.MQ = (int)std::min<int64_t>(std::max<int64_t>(max_m, 1) + 2, RSD_MQ_MAX);
+    pv.NB = 34 * pv.MQ;
     RSD_OK_OR_RETURN(plan_groups.ensure(sizeof(int2) * (size_t)n_pairs));
     int *bins = (int *)plan_bins.p;
     pv.pair_bin = (int *)plan_pair_bin.p;
     pv.bin_cnt = bins;
-    pv.bin_cursor = bins + (RSD_NB + 1);
-    pv.bin_group_off = bins + 2 * (RSD_NB + 1);
-    pv.bin_warp_off = bins + 3 * (RSD_NB + 1);
-    pv.totals = bins + 4 * (RSD_NB + 1);
+    // fixed array bases (independent of this call's NB) so the zeroed-counter invariant survives a change of NB
+    pv.bin_cursor = bins + (RSD_NB_MAX + 1);
+    pv.bin_group_off = bins + 2 * (RSD_NB_MAX + 1);
+    pv.bin_warp_off = bins + 3 * (RSD_NB_MAX + 1);
+    pv.totals = bins + 4 * (RSD_NB_MAX + 1);
     pv.work_counter = pv.totals + 4;
     pv.groups = (int2 *)plan_groups.p;
     pv.C = C; pv.allow_twin = allow_twin;
-    RSD_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)(4 * (RSD_NB + 1) + 8), st));
-    RSD_CUDA(cudaMemsetAsync(pv.groups, 0xFF, sizeof(int2) * (size_t)n_pairs, st));
+    // bin counters are left zeroed by k_plan_fill; cursors / ticket / odd-twin slots are reset by
+    // k_plan_scan — so a plan is three kernels and no memsets.  A call that failed between count and
+    // fill leaves them dirty: start clean then.
+    if (plan_dirty) {
+        RSD_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8), st));
+    }
+    plan_dirty = true;
     const int T = 256;
     const unsigned G = (unsigned)((n_pairs + T - 1) / T);
     k_plan_count<<<G, T, 0, st>>>(d_alen, d_blen, n_pairs, pv, ins, del, d_out);
@@ -287,6 +306,7 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     k_plan_fill<<<G, T, 0, st>>>(n_pairs, pv);
     launches += 3;
     RSD_CUDA(cudaGetLastError());
+    plan_dirty = false;
     return RSD_OK;
 }
 
@@ -295,9 +315,12 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
 // ------------------------------------------------------------------------------------------------
 template <typename K>
 static int persistent_grid(K kernel, int threads, int sm_count, int &blocks) {
+    static thread_local const void *cached_k[16]; static thread_local int cached_v[16]; static thread_local int n_cached = 0;
+    for (int i = 0; i < n_cached; ++i) if (cached_k[i] == (const void *)kernel) { blocks = cached_v[i] * sm_count; return RSD_OK; }
     int per_sm = 0;
     RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
     if (per_sm < 1) per_sm = 1;
+    if (n_cached < 16) { cached_k[n_cached] = (const void *)kernel; cached_v[n_cached] = per_sm; ++n_cached; }
     blocks = per_sm * sm_count;
     return RSD_OK;
 }
@@ -312,9 +335,9 @@ int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const
     ModeInfo mi;
     RSD_OK_OR_RETURN(classify(symmask, max_m, max_n, bits, force_mode, mi));
     if (mode_out) *mode_out = mi.mode;
-    timed = false;
+    timed = false; last_ms_override = 0.0;
     if (n_pairs == 0) return RSD_OK;
-    RSD_OK_OR_RETURN(upload_costs(mi, st));
+    if (!costs_preloaded) RSD_OK_OR_RETURN(upload_costs(mi, st));
     SeqView A{a_words, a_start, a_len}, B{b_words, b_start, b_len};
     PlanView pv;
     constexpr int THREADS = 128;
@@ -322,44 +345,44 @@ int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const
     int blocks = 0;
     if (mi.mode == RSD_MODE_I16X2) {
         constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 1, d_out, st, pv));
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 1, d_out, st, pv, max_m));
         RSD_OK_OR_RETURN(persistent_grid(k_dist_twin16<C>, THREADS, sm_count, blocks));
         const int stride = max_n > 32 * C ? (int)max_m : 0;
         RSD_OK_OR_RETURN(scratch.ensure(sizeof(uint32_t) * (size_t)stride * blocks * wpb + 16));
-        if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+        if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
         k_dist_twin16<C><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)scratch.p, stride, 1u);
     } else if (mi.mode == RSD_MODE_I32) {
         constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv));
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m));
         const int stride = max_n > 32 * C ? (int)max_m : 0;
         if (bits == 2) {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 2, C>, THREADS, sm_count, blocks));
             RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * (size_t)stride * blocks * wpb + 16));
-            if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+            if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<int, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
         } else {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 4, C>, THREADS, sm_count, blocks));
             RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * (size_t)stride * blocks * wpb + 16));
-            if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+            if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<int, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
         }
     } else {
         constexpr int C = 16;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv));
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m));
         const int stride = max_n > 32 * C ? (int)max_m : 0;
         if (bits == 2) {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 2, C>, THREADS, sm_count, blocks));
             RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * (size_t)stride * blocks * wpb + 16));
-            if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+            if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<double, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
         } else {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 4, C>, THREADS, sm_count, blocks));
             RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * (size_t)stride * blocks * wpb + 16));
-            if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+            if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<double, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
         }
     }
-    if (timing) { RSD_CUDA(cudaEventRecord(ev1, st)); timed = true; }
+    if (timing) { RSD_CUDA(cudaEventRecord(cur_ev1, st)); timed = true; }
     launches += 1;
     RSD_CUDA(cudaGetLastError());
     return RSD_OK;
@@ -397,7 +420,7 @@ int rsd_ctx::upload_seqs(SeqBufs &sb, const uint32_t *words, const int64_t *star
 extern "C" int rsd_distance_batch(rsd_ctx *c,
                                   const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
                                   const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
-                                  int64_t n_pairs, int bits, uint32_t symmask, int force_mode,
+                                  int64_t n_pairs, int64_t max_m_hint, int64_t max_n_hint, int bits, uint32_t symmask, int force_mode,
                                   double *out, int *mode_out) {
     if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
     if (n_pairs < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: n_pairs < 0");
@@ -405,17 +428,103 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
         return rsd_fail(RSD_EINVAL, "rsd_distance_batch: NULL buffer");
     RSD_OK_OR_RETURN(c->ensure_device());
     if (n_pairs == 0) return RSD_OK;
-    cudaStream_t st = c->stream;
-    RSD_OK_OR_RETURN(c->upload_seqs(c->bufA, a_words, a_start, a_len, n_pairs, a_nwords, st));
-    RSD_OK_OR_RETURN(c->upload_seqs(c->bufB, b_words, b_start, b_len, n_pairs, b_nwords, st));
+    const bool trace = getenv("RSD_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_in = now();
+    double t_len = 0, t_cost = 0, t_copy = 0, t_comp = 0;
+    cudaStream_t st = c->stream, cp = c->copy_stream;
+    const int64_t max_m = max_m_hint > 0 ? max_m_hint : max_len(a_len, n_pairs);
+    const int64_t max_n = max_n_hint > 0 ? max_n_hint : max_len(b_len, n_pairs);
+    // Large batches are cut into chunks of pairs so the H2D copy of chunk k+1 (copy stream) overlaps
+    // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
+    // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
+    t_len = now();
+    // Three chunks whose sizes grow geometrically (1:2:4): the first copy is short, and because compute is slower
+    // than the copy no later chunk ever waits for its data.
+    int n_chunks = 1;
+    int64_t bounds[RSD_MAX_CHUNKS + 1];
+    bounds[0] = 0;
+    if (n_pairs >= (1 << 16)) {
+        n_chunks = 3;
+        double wsum = 0, w = 1.0, acc = 0;
+        for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= 2.0; }
+        w = 1.0;
+        for (int k = 0; k < n_chunks; ++k) { acc += w; w *= 2.0; bounds[k + 1] = (int64_t)((double)n_pairs * acc / wsum); }
+    }
+    bounds[n_chunks] = n_pairs;
+    // costs go up first: a small pageable copy issued later would queue behind the big H2D copies on
+    // the copy engine and stall the first kernel until every chunk has arrived.
+    {
+        ModeInfo mi0;
+        RSD_OK_OR_RETURN(c->classify(symmask, max_m, max_n, bits, force_mode, mi0));
+        RSD_OK_OR_RETURN(c->upload_costs(mi0, st));
+    }
+    t_cost = now();
+    SeqBufs &dA = c->bufA, &dB = c->bufB;
+    RSD_OK_OR_RETURN(dA.words.ensure(sizeof(uint32_t) * (size_t)(a_nwords + 8)));
+    RSD_OK_OR_RETURN(dA.start.ensure(sizeof(int64_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(dA.len.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(dB.words.ensure(sizeof(uint32_t) * (size_t)(b_nwords + 8)));
+    RSD_OK_OR_RETURN(dB.start.ensure(sizeof(int64_t) * (size_t)n_pairs));
+    RSD_OK_OR_RETURN(dB.len.ensure(sizeof(int32_t) * (size_t)n_pairs));
     RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_pairs));
-    const int64_t max_m = max_len(a_len, n_pairs), max_n = max_len(b_len, n_pairs);
-    RSD_OK_OR_RETURN(c->distance_dev((const uint32_t *)c->bufA.words.p, (const int64_t *)c->bufA.start.p,
-                                     (const int32_t *)c->bufA.len.p, (const uint32_t *)c->bufB.words.p,
-                                     (const int64_t *)c->bufB.start.p, (const int32_t *)c->bufB.len.p, n_pairs, max_m,
-                                     max_n, bits, symmask, force_mode, (double *)c->out_f64.p, mode_out, st));
-    RSD_CUDA(cudaMemcpyAsync(out, c->out_f64.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaMemsetAsync((uint32_t *)dA.words.p + a_nwords, 0, sizeof(uint32_t) * 8, cp));
+    RSD_CUDA(cudaMemsetAsync((uint32_t *)dB.words.p + b_nwords, 0, sizeof(uint32_t) * 8, cp));
+    // the previous call's kernels may still read these buffers: order the copy stream after them
+    RSD_CUDA(cudaEventRecord(c->ev_sync, st));
+    RSD_CUDA(cudaStreamWaitEvent(cp, c->ev_sync, 0));
+    RSD_CUDA(cudaEventRecord(c->ev_begin, cp));
+    const bool timing = c->timing;
+    float kernel_ms = 0.f;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+        if (p1 <= p0) continue;
+        const int64_t aw0 = a_start[p0], aw1 = p1 < n_pairs ? a_start[p1] : a_nwords;
+        const int64_t bw0 = b_start[p0], bw1 = p1 < n_pairs ? b_start[p1] : b_nwords;
+        RSD_CUDA(cudaMemcpyAsync((uint32_t *)dA.words.p + aw0, a_words + aw0, sizeof(uint32_t) * (size_t)(aw1 - aw0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaMemcpyAsync((uint32_t *)dB.words.p + bw0, b_words + bw0, sizeof(uint32_t) * (size_t)(bw1 - bw0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaMemcpyAsync((int64_t *)dA.start.p + p0, a_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaMemcpyAsync((int64_t *)dB.start.p + p0, b_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaMemcpyAsync((int32_t *)dA.len.p + p0, a_len + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaMemcpyAsync((int32_t *)dB.len.p + p0, b_len + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
+    }
+    t_copy = now();
+    for (int k = 0; k < n_chunks; ++k) {
+        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+        if (p1 <= p0) continue;
+        RSD_CUDA(cudaStreamWaitEvent(st, c->ev_chunk[k], 0));
+        c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k]; c->costs_preloaded = true;
+        int rc = c->distance_dev((const uint32_t *)dA.words.p, (const int64_t *)dA.start.p + p0, (const int32_t *)dA.len.p + p0,
+                                 (const uint32_t *)dB.words.p, (const int64_t *)dB.start.p + p0, (const int32_t *)dB.len.p + p0,
+                                 p1 - p0, max_m, max_n, bits, symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st);
+        c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; c->costs_preloaded = false;
+        if (rc) return rc;
+        RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, st));
+    }
+    t_comp = now();
     RSD_CUDA(cudaStreamSynchronize(st));
+    if (trace) fprintf(stderr, "[rsd trace] host ms: max_len %.3f, classify+costs %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
+                       t_len - t_in, t_cost - t_len, t_copy - t_cost, t_comp - t_copy, now() - t_comp);
+    if (timing) {
+        for (int k = 0; k < n_chunks; ++k) {
+            if (bounds[k + 1] <= bounds[k]) continue;
+            float ms = 0.f;
+            RSD_CUDA(cudaEventElapsedTime(&ms, c->ev_t0[k], c->ev_t1[k]));
+            kernel_ms += ms;
+        }
+        c->timed = false; c->last_ms_override = kernel_ms;
+        if (getenv("RSD_TRACE")) {
+            for (int k = 0; k < n_chunks; ++k) {
+                float a = 0, b = 0, d = 0;
+                cudaEventElapsedTime(&a, c->ev_begin, c->ev_chunk[k]);
+                cudaEventElapsedTime(&b, c->ev_begin, c->ev_t0[k]);
+                cudaEventElapsedTime(&d, c->ev_begin, c->ev_t1[k]);
+                fprintf(stderr, "[rsd trace] chunk %d pairs %lld: copy done %.3f ms, kernel %.3f -> %.3f ms\n", k,
+                        (long long)(bounds[k + 1] - bounds[k]), a, b, d);
+            }
+        }
+    }
     return RSD_OK;
 }
 
@@ -613,7 +722,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         SeqView A{dA, sA + p0, lA + p0}, B{dB, sB + p0, lB + p0};
         PlanView pv;
         // trivial pairs (m == 0 or n == 0) get their distance from the planner and an all-INS / all-DEL script from the traceback
-        RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv));
+        RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv, max_m));
         ScriptView sv{(uint32_t *)dirs.p, (const int64_t *)misc.p + p0, (double *)out_f64.p + p0};
         if (f64) {
             if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
@@ -921,12 +1030,12 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     for (int64_t j = 0; j < n; ++j) { if (b[j] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pair: code > 15"); symmask |= 1u << b[j]; }
     ModeInfo mi;
     RSD_OK_OR_RETURN(c->classify(symmask, m, n, 4, force_mode == RSD_MODE_I16X2 ? RSD_MODE_I32 : force_mode, mi));
-    // int64 keys: cost * 2^S + steps must stay below 2^62
+    // integer keys (cost * 2^S + steps) are carried in doubles: they must stay below 2^52
     const int S = ceil_log2_i64(m + n + 66);
     bool f64 = mi.mode == RSD_MODE_F64;
     if (!f64) {
         const double bound = ((double)m * mi.ic.del + (double)(n + 512) * mi.ic.ins + 4.0 * ((double)mi.ic.ins + mi.ic.del)) * std::ldexp(1.0, S);
-        if (bound > 4.0e18) { if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_long_pair: int64 key would overflow"); f64 = true; }
+        if (bound > 4.0e15) { if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_long_pair: int64 key would overflow"); f64 = true; }
     } else if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_EINVAL, "rsd_long_pair: integer mode not exact for these costs");
     if (mode_out) *mode_out = f64 ? RSD_MODE_F64 : RSD_MODE_I32;
     c->timed = false;
@@ -966,7 +1075,10 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     la.progress = (int *)((unsigned char *)c->scratch.p + (size_t)n_panels * (size_t)m * 12);
     la.dist = (double *)c->out_f64.p;
     la.S = S;
-    RSD_CUDA(cudaMemsetAsync(la.progress, 0, (size_t)n_panels * 4, st));
+    la.dbg = nullptr;
+    const bool ltrace = getenv("RSD_TRACE") != nullptr;
+    if (ltrace) { RSD_OK_OR_RETURN(c->misc.ensure((size_t)n_panels * 64)); la.dbg = (unsigned long long *)c->misc.p; }
+    RSD_CUDA(cudaMemsetAsync(la.bound, 0x80, (size_t)n_panels * (size_t)m * 8, st));      // sentinel = "not published yet"
     const IntCosts *dic = c->d_ic; const F64Costs *dfc = c->d_fc;
     void *args[] = {&la, &dic, &dfc};
     if (c->timing) RSD_CUDA(cudaEventRecord(c->ev0, st));
@@ -987,6 +1099,14 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     if (c->timing) { RSD_CUDA(cudaEventRecord(c->ev1, st)); c->timed = true; }
     RSD_CUDA(cudaGetLastError());
     RSD_CUDA(cudaMemcpyAsync(dist, c->out_f64.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ltrace) {
+        std::vector<unsigned long long> d((size_t)n_panels * 8);
+        RSD_CUDA(cudaMemcpyAsync(d.data(), la.dbg, d.size() * 8, cudaMemcpyDeviceToHost, st));
+        RSD_CUDA(cudaStreamSynchronize(st));
+        for (int w2 = 0; w2 < n_panels; w2 += std::max(1, n_panels / 8))
+            fprintf(stderr, "[rsd trace] panel %d: start +%.3f ms, end +%.3f ms, Mclk: poll %.3f publish %.3f a-loads %.3f rows %.3f\n", w2,
+                    (d[w2 * 8] - d[0]) * 1e-6, (d[w2 * 8 + 1] - d[0]) * 1e-6, d[w2 * 8 + 2] * 1e-6, d[w2 * 8 + 3] * 1e-6, d[w2 * 8 + 4] * 1e-6, d[w2 * 8 + 5] * 1e-6);
+    }
     int32_t k32 = 0;
     if (want_script) {
         RSD_CUDA(cudaMemcpyAsync(&k32, c->s_nops.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -10,6 +10,8 @@
 
 int rsd_fail(int code, const char *fmt, ...);
 
+#define RSD_MAX_CHUNKS 8
+
 #define RSD_CUDA(call)                                                                              \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \
@@ -62,7 +64,12 @@ struct rsd_ctx {
     bool inited = false;
     pid_t pid = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_sync = nullptr, ev_chunk[RSD_MAX_CHUNKS] = {}, ev_t0[RSD_MAX_CHUNKS] = {}, ev_t1[RSD_MAX_CHUNKS] = {};
+    cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr;
+    double last_ms_override = 0.0;
+    bool costs_preloaded = false;
+    bool plan_dirty = true;      // bin counters need a memset before the next plan
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
     int64_t launches = 0;
@@ -91,7 +98,7 @@ struct rsd_ctx {
     int upload_seqs(SeqBufs &sb, const uint32_t *words, const int64_t *start, const int32_t *len, int64_t n,
                     int64_t n_words, cudaStream_t st);
     int make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin, double *d_out,
-                  cudaStream_t st, PlanView &pv);
+                  cudaStream_t st, PlanView &pv, int64_t max_m);
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);

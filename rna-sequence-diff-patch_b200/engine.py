@@ -85,7 +85,7 @@ class Engine:
         check(self._lib.rsd_distance_batch(
             self._ctx, ptr(A.words, _u32), ptr(A.start, _i64), ptr(A.len, _i32), A.words.shape[0],
             ptr(B.words, _u32), ptr(B.start, _i64), ptr(B.len, _i32), B.words.shape[0],
-            A.n, bits, A.symmask | B.symmask, force_mode, ptr(out, _f64), C.byref(mode)))
+            A.n, A.max_len, B.max_len, bits, A.symmask | B.symmask, force_mode, ptr(out, _f64), C.byref(mode)))
         self.last_mode = mode.value
         return out
 

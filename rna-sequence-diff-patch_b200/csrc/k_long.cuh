@@ -180,7 +180,7 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
                         left = H[c];
                         code = p_ins ? 0u : (p_del ? 1u : 2u);
                     }
-                    acc[c] = __funnelshift_r(acc[c], code, 2);
+                    acc[c] = (acc[c] << 2) | (code == 0u ? 0u : code + 1u);      // layout of k_script.cuh: 00 INS, 10 DEL, 11 UPD
                 }
                 last = left; prev_recv = recv;
                 if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
@@ -189,7 +189,7 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
                     uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
 #pragma unroll
                     for (int c = 0; c < C; c += 4)
-                        dst[c >> 2] = make_uint4(acc[c] >> sh, acc[c + 1] >> sh, acc[c + 2] >> sh, acc[c + 3] >> sh);
+                        dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
                 }
             }
             // lane 31 owns the panel's right-most column (row t-31 at this step): park it for the block-end store
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint3
             const int i_min = rb_lo * 16;
             while (i > i_min && j > c_lo) {
                 const uint32_t wv = tile[((i - 1) >> 4) - rb_lo][(j - 1) - c_lo];
-                const uint32_t code = (wv >> (2 * ((i - 1) & 15))) & 3u;
+                const uint32_t code = dir_decode(wv, i - 1);
                 tmp[--pos] = (uint8_t)code;
                 if (code == 0u) --j; else if (code == 1u) --i; else { --i; --j; }
             }

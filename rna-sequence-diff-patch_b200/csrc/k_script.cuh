@@ -13,11 +13,21 @@
 // where the "- 1" is the diagonal edge saving one step against INS+DEL.  Ties are resolved INS,
 // DEL, UPD by the order of the two min instructions (VIMNMX with predicate = __vibmin_s32).
 //
-// Direction storage: dirs[pair][rb][col] is one u32 holding rows 16*rb .. 16*rb+15 of column col
-// (2 bits each, row r at bits 2*(r & 15)); col < n_pad = strips * C.  Codes: 0 INS, 1 DEL, 2 UPD.
+// Direction storage: dirs[pair][rb][col] is one u32 holding rows 16*rb .. 16*rb+15 of column col,
+// two bits per row pushed in from the right (row r sits at bits 2*(15 - (r & 15)) + {1,0});
+// col < n_pad = strips * C.  Bit 1 = "not INS" (the left candidate lost), bit 0 = "UPD rather than DEL"
+// (the diagonal candidate beat the upper one): 0x -> INS, 10 -> DEL, 11 -> UPD.  In the integer kernel
+// both bits are sign bits of differences the recurrence already has (t2 - left, t2 - up), shifted in
+// with one funnel shift each — no compare, no select.
 #pragma once
 #include <type_traits>
 #include "k_dist.cuh"
+
+// direction word -> op code (0 INS, 1 DEL, 2 UPD) of matrix row `row` (0-based interior row)
+__device__ __forceinline__ uint32_t dir_decode(uint32_t word, int row) {
+    const uint32_t bits = (word >> (2 * (15 - (row & 15)))) & 3u;
+    return bits < 2u ? 0u : bits - 1u;
+}
 
 struct ScriptView {
     uint32_t *dirs;            // chunk-local direction words
@@ -31,11 +41,11 @@ template <bool F64, int BITS, int C>
 __global__ void __launch_bounds__(128)
 k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
              const F64Costs *__restrict__ fcp, ScriptView sv, int S,
-             void *__restrict__ scratch_v, int scratch_stride) {
+             void *__restrict__ scratch_v, int scratch_stride, int minus_one) {
     using T = typename std::conditional<F64, double, int>::type;
     constexpr int PER = 32 / BITS;
     static_assert(C % PER == 0 && C % 4 == 0, "strip width");
-    __shared__ T s_w[256];
+    __shared__ __align__(2048) T s_w[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         if constexpr (F64) s_w[k] = fcp->sub[k >> 4][k & 15];
         else s_w[k] = (int)(((unsigned)icp->w[k >> 4][k & 15] << S) - 1u);     // (w << S) - 1
@@ -86,6 +96,11 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
 #pragma unroll
                 for (int c = 0; c < PER; ++c) bc[k * PER + c] = (x >> (BITS * c)) & ((1u << BITS) - 1u);
             }
+            if constexpr (!F64) {      // int path: keep the column's shared-memory byte address, OR the row offset in later
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase | ((uint32_t)bc[c] << 2));
+            }
             T H[C];
             int HS[F64 ? C : 1];
             uint32_t acc[C];
@@ -127,9 +142,11 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     }
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const T w = s_w[rowbase + bc[c]];
-                        uint32_t code;
+                        T w;
+                        if constexpr (F64) w = s_w[rowbase + bc[c]];
+                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] | ((uint32_t)rowbase << 2)));
                         if constexpr (F64) {
+                            uint32_t code;
                             const double c0 = __dadd_rn(left, c_ins);
                             const double c1 = __dadd_rn(H[c], c_del);
                             const double c2 = __dadd_rn(diag, w);
@@ -141,26 +158,28 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                             diag = H[c]; diag_s = HS[c];
                             H[c] = v; HS[c] = bs;
                             left = v; left_s = bs;
+                            acc[c] = (acc[c] << 2) | (code == 0u ? 0u : code + 1u);      // 0 -> 00, 1 -> 10, 2 -> 11
                         } else {
-                            bool p_del, p_ins;
-                            const int x = diag + w;
-                            const int t2 = __vibmin_s32(H[c], x, &p_del);     // up <= diag + w  -> DEL before UPD
-                            diag = H[c];
-                            H[c] = __vibmin_s32(left, t2, &p_ins);           // left <= rest    -> INS first
+                            const int up = H[c];
+                            const int t2 = addmin32(diag, w, up);              // min(diag + w, up): ties keep DEL
+                            const int d_upd = sub_fma(t2, up, minus_one);      // < 0  <=>  diagonal strictly better than up
+                            const int d_ins = sub_fma(t2, left, minus_one);    // < 0  <=>  left loses (ties keep INS)
+                            diag = up;
+                            H[c] = min(t2, left);
                             left = H[c];
-                            code = p_ins ? 0u : (p_del ? 1u : 2u);
+                            acc[c] = __funnelshift_l((uint32_t)d_ins, acc[c], 1);   // sign bits shifted in: "not INS",
+                            acc[c] = __funnelshift_l((uint32_t)d_upd, acc[c], 1);   // then "UPD rather than DEL"
                         }
-                        acc[c] = __funnelshift_r(acc[c], code, 2);           // row i lands at bits 2*(i&15)
                     }
                     last = left; prev_recv = recv;
                     if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
                     if (wr_scr) { scr[i] = last; if constexpr (F64) scr_steps[i] = last_s; }
                     if ((i & 15) == 15 || i == m - 1) {
-                        const int sh = 2 * (15 - (i & 15));                  // partial last block
+                        const int sh = 2 * (15 - (i & 15));                  // partial last block: align as if 16 rows
                         uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * n_pad);
 #pragma unroll
                         for (int c = 0; c < C; c += 4)
-                            dst[c >> 2] = make_uint4(acc[c] >> sh, acc[c + 1] >> sh, acc[c + 2] >> sh, acc[c + 3] >> sh);
+                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
                     }
                 }
             }
@@ -204,7 +223,7 @@ __global__ void k_traceback(const int32_t *__restrict__ a_len, const int32_t *__
     int i = m, j = n;
     while (i > 0 && j > 0) {
         const uint32_t w = d[(size_t)((i - 1) >> 4) * n_pad + (j - 1)];
-        const uint32_t code = (w >> (2 * ((i - 1) & 15))) & 3u;
+        const uint32_t code = dir_decode(w, i - 1);
         slot[--pos] = (uint8_t)code;
         if (code == 0u) --j; else if (code == 1u) --i; else { --i; --j; }
     }

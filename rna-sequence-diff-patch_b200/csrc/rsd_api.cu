@@ -654,7 +654,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b) maxabsw = std::max<int64_t>(maxabsw, std::llabs((long long)mi.ic.w[a][b]));
         const double bound = ((double)max_m * mi.ic.del + (double)(max_n + 64) * mi.ic.ins + (double)maxabsw + 2.0) * std::ldexp(1.0, S)
                              + (double)(max_m + max_n + 66);
-        if (bound >= 2147483000.0) {
+        if (bound >= 1073741000.0) {          // < 2^30: differences of two keys must not overflow either
             if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_script: int32 (cost,steps) key would overflow for these lengths");
             mode = RSD_MODE_F64;
         }
@@ -725,11 +725,11 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv, max_m));
         ScriptView sv{(uint32_t *)dirs.p, (const int64_t *)misc.p + p0, (double *)out_f64.p + p0};
         if (f64) {
-            if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
-            else k_script_fwd<true, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+            if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
+            else k_script_fwd<true, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
         } else {
-            if (bits == 2) k_script_fwd<false, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
-            else k_script_fwd<false, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride);
+            if (bits == 2) k_script_fwd<false, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
+            else k_script_fwd<false, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
         }
         k_traceback<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(lA + p0, lB + p0, np, (const uint32_t *)dirs.p,
                                                                (const int64_t *)misc.p + p0, C, (uint8_t *)s_tmp.p, max_ops,

@@ -52,6 +52,12 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
     return r;
 }
+// a - b as b * (-1) + a on the fma pipe (`minus_one` is an opaque kernel argument equal to -1)
+__device__ __forceinline__ int sub_fma(int a, int b, int minus_one) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(minus_one), "r"(a));
+    return r;
+}
 __device__ __forceinline__ uint32_t max3u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ int addmin32(int a, int b, int c) { return __viaddmin_s32(a, b, c); }
 

@@ -12,6 +12,9 @@ Layout:
   engine.py    Engine: costs, batched distance / script / patch / search
   sed.py       the StringEditDistance.py module surface on top of Engine
   ir.py        IRMethods.wf_score / search_collection / top-k on top of Engine
+  ingest.py    FASTA / SeqXML -> packed database (T->U, X->N like the reference's importers)
+  eswire.py    edit-script JSON export/import, packed <-> dict scripts, reverse on packed scripts
+  dist_search.py  database search sharded over the GPUs of one box (one all_gather)
   dropin/      modules importable as `StringEditDistance` / `IRMethods` + cost files
 """
 from ._lib import RsdError, load_library, library_path  # noqa: F401

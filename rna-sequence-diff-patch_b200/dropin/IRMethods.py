@@ -33,5 +33,23 @@ def search_collection(query, vector_type, collection, method, return_dict=None, 
         return scores
 
 
+def create_search_threads(methods_to_execute, query, vector_type, collection, on_search_done=None, on_wf_done=None):
+    """IR:480-515 for the Wagner-Fischer method: ONE scan of the collection on the GPU instead of the
+    reference's forked process per method plus a second, separate WF pass (IR:487-491,511-515); no
+    pandas (the reference's DataFrame.append, IR:501, no longer exists).  The callbacks receive what
+    the reference passes them: a list of (sequence, mean score) and the raw wf_score list."""
+    others = [m for m in methods_to_execute if m is not wf_score]
+    if others:
+        raise NotImplementedError("this drop-in serves the wf_score search only")
+    scores = search_collection(query, vector_type, collection, wf_score)
+    if on_search_done is not None:
+        merged = {}
+        for seq, sc in scores:                      # duplicates collapse like the reference's dict (IR:501)
+            merged[seq] = sc
+        on_search_done(list(merged.items()))
+    if wf_score in methods_to_execute and on_wf_done is not None:
+        on_wf_done(scores)
+
+
 def top_k(scores, k):
     return _ir.top_k(scores, k)

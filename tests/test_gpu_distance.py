@@ -214,5 +214,14 @@ def test_wf_score_and_search_collection_g7(R, golden):
             assert [list(x) for x in IR.top_k(scores, 6)] == c["top6"]
         for a, b, v in golden["wf_score_user"]:
             assert IR.wf_score(a, b, True) == v
+        # create_search_threads replacement (IR:480-515): one GPU scan, both callbacks, packed-DB collection
+        from rna_sequence_diff_patch_b200.ingest import SequenceDB
+        db = SequenceDB(dict(zip(golden["xml_ids"], golden["xml_seqs"])))
+        got = {}
+        IR.create_search_threads([IR.wf_score], golden["G7"][0]["query"], 'tf', db,
+                                 on_search_done=lambda r: got.__setitem__("mean", r),
+                                 on_wf_done=lambda r: got.__setitem__("wf", r))
+        assert [list(x) for x in got["wf"]] == golden["G7"][0]["scores"]
+        assert [list(x) for x in IR.top_k(got["mean"], 6)] == golden["G7"][0]["top6"]
     finally:
         os.chdir(cwd)

@@ -1,0 +1,59 @@
+"""Host-side 'next rows': ingest (FASTA / SeqXML -> packed DB) and edit-script wire formats. CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as G
+    G.build()
+    import rna_sequence_diff_patch_b200 as R
+    from rna_sequence_diff_patch_b200 import eswire, ingest, sed
+    return R, eswire, ingest, sed
+
+
+def test_seqxml_and_fasta_ingest(pkg, golden, tmp_path):
+    R, eswire, ingest, sed = pkg
+    xml = tmp_path / "in.xml"
+    dna = [s.replace("U", "T") for s in golden["xml_seqs"]]           # test_input.xml holds DNA letters
+    xml.write_text('<?xml version="1.0"?>\n<seqXML>\n' + "\n".join(
+        f'  <entry id="{i}" >\n    <RNAseq>{s}</RNAseq>\n  </entry>' for i, s in zip(golden["xml_ids"], dna)) + "\n</seqXML>\n")
+    recs = ingest.read_seqxml(str(xml))
+    assert list(recs.keys()) == golden["xml_ids"] and list(recs.values()) == golden["xml_seqs"]
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(f">{i} some description\n{s[:10]}\n{s[10:]}\n" for i, s in zip(golden["xml_ids"], dna)) + ">last\nACGTX\n")
+    recs = ingest.read_fasta(str(fa))
+    assert list(recs.values())[:-1] == golden["xml_seqs"] and recs["last"] == "ACGUN"
+    db = ingest.SequenceDB.from_file(str(xml))
+    assert len(db) == 25 and [d["sequence"] for d in db.find({})] == golden["xml_seqs"]
+    from rna_sequence_diff_patch_b200.encoding import unpack
+    codes, off = unpack(db.packed)
+    assert O.decode(codes[off[3]:off[4]]) == golden["xml_seqs"][3]
+
+
+def test_es_json_roundtrip_and_packed_conversions(pkg, golden, tmp_path):
+    R, eswire, ingest, sed = pkg
+    n = 0
+    for c in golden["small"] + golden["medium"]:
+        if "es" not in c:
+            continue
+        es = c["es"][0]
+        path = tmp_path / "es.json"
+        eswire.dump_es(es, str(path))
+        assert path.read_text() == json.dumps({"edit_script": es}, indent=4)       # gui.py:636-639
+        assert eswire.load_es(str(path)) == es
+        op, oi, oj = eswire.es_to_packed(es)
+        ops, ooi, ooj, _ = O.canonical_script(c["a"], c["b"], golden["user_costs" if c["user"] else "default_costs"])
+        assert np.array_equal(op, ops) and np.array_equal(oi, ooi) and np.array_equal(oj, ooj)
+        assert eswire.packed_to_es(op, oi, oj, c["a"], c["b"]) == es
+        assert eswire.rev_es_from_packed(op, oi, oj, c["a"], c["b"]) == c["rev0"]  # == generate_rev_es(es)
+        rop, roi, roj = eswire.rev_packed(op, oi, oj)                              # packed B -> A script
+        code, back = O.patch_closed_codes(rop, roi, roj, O.encode(c["b"]), O.encode(c["a"]), O.encode(c["b"]))
+        assert code == 0 and O.decode(back) == c["a"]
+        n += 1
+    assert n > 250

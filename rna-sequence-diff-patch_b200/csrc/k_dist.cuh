@@ -237,6 +237,11 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
 #pragma unroll
                 for (int c = 0; c < PER; ++c) bc[k * PER + c] = (x >> (BITS * c)) & ((1u << BITS) - 1u);
             }
+            {   // keep each column's shared-memory byte address; the row offset is added per row (one add per lookup)
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase + (uint32_t)bc[c] * (uint32_t)sizeof(T));
+            }
             T H[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -260,7 +265,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                 }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
-                    const int rowbase = (cur & ((1u << BITS) - 1u)) << 4; cur >>= BITS;
+                    const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)sizeof(T); cur >>= BITS;
                     T left = recv, diag = prev_recv;
                     if constexpr (F64) {
                         if (i == 0) diag = (s == 0) ? 0.0 : __dmul_rn((double)col0, c_ins);   // row-0 border
@@ -268,13 +273,15 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                     }
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const T w = s_w[rowbase + bc[c]];
+                        T w;
+                        if constexpr (F64) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"((uint32_t)bc[c] + rowoff));
+                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] + rowoff));
                         if constexpr (F64) {
                             const double c0 = __dadd_rn(left, c_ins);      // SED:95
                             const double c1 = __dadd_rn(H[c], c_del);      // SED:97
                             const double c2 = __dadd_rn(diag, w);          // SED:99
                             diag = H[c];
-                            H[c] = fmin(fmin(c0, c1), c2);                 // SED:106-107
+                            H[c] = dmin2(dmin2(c0, c1), c2);                 // SED:106-107
                         } else {
                             const int t2 = addmin32(diag, w, H[c]);
                             diag = H[c];

@@ -30,7 +30,7 @@ k_matrix_f64(const uint8_t *__restrict__ a, int m, const uint8_t *__restrict__ b
             const double c0 = __dadd_rn(D[(size_t)i * W + j - 1], ins);   // SED:95
             const double c1 = __dadd_rn(D[(size_t)(i - 1) * W + j], del); // SED:97
             const double c2 = __dadd_rn(D[(size_t)(i - 1) * W + j - 1], sub); // SED:99
-            const double v = fmin(fmin(c0, c1), c2);
+            const double v = dmin2(dmin2(c0, c1), c2);
             D[(size_t)i * W + j] = v;
             mask[(size_t)i * W + j] = (uint8_t)((c0 == v) | ((c1 == v) << 1) | ((c2 == v) << 2)); // SED:109
         }

@@ -45,7 +45,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
     using T = typename std::conditional<F64, double, int>::type;
     constexpr int PER = 32 / BITS;
     static_assert(C % PER == 0 && C % 4 == 0, "strip width");
-    __shared__ __align__(2048) T s_w[256];
+    __shared__ T s_w[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         if constexpr (F64) s_w[k] = fcp->sub[k >> 4][k & 15];
         else s_w[k] = (int)(((unsigned)icp->w[k >> 4][k & 15] << S) - 1u);     // (w << S) - 1
@@ -96,10 +96,10 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
 #pragma unroll
                 for (int c = 0; c < PER; ++c) bc[k * PER + c] = (x >> (BITS * c)) & ((1u << BITS) - 1u);
             }
-            if constexpr (!F64) {      // int path: keep the column's shared-memory byte address, OR the row offset in later
+            if constexpr (!F64) {      // int path: keep the column's shared-memory byte address, add the row offset later
                 const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
 #pragma unroll
-                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase | ((uint32_t)bc[c] << 2));
+                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase + ((uint32_t)bc[c] << 2));
             }
             T H[C];
             int HS[F64 ? C : 1];
@@ -144,14 +144,14 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     for (int c = 0; c < C; ++c) {
                         T w;
                         if constexpr (F64) w = s_w[rowbase + bc[c]];
-                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] | ((uint32_t)rowbase << 2)));
+                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] + ((uint32_t)rowbase << 2)));
                         if constexpr (F64) {
                             uint32_t code;
                             const double c0 = __dadd_rn(left, c_ins);
                             const double c1 = __dadd_rn(H[c], c_del);
                             const double c2 = __dadd_rn(diag, w);
                             const int s0 = left_s + 1, s1 = HS[c] + 1, s2 = diag_s + 1;
-                            const double v = fmin(fmin(c0, c1), c2);
+                            const double v = dmin2(dmin2(c0, c1), c2);
                             int bs = (c0 == v) ? s0 : 0x7fffffff; code = 0u;
                             if (c1 == v && s1 < bs) { bs = s1; code = 1u; }
                             if (c2 == v && s2 < bs) { bs = s2; code = 2u; }

@@ -61,6 +61,9 @@ __device__ __forceinline__ int sub_fma(int a, int b, int minus_one) {
 __device__ __forceinline__ uint32_t max3u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ int addmin32(int a, int b, int c) { return __viaddmin_s32(a, b, c); }
 
+// min of two non-NaN doubles as compare + select (fmin() also pays for NaN quieting: ~7 instructions)
+__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
+
 __device__ __forceinline__ int warp_max(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(RSD_FULL, v, o));

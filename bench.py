@@ -114,6 +114,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c2-iupac"])
     ap.add_argument("--pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short C3/C4/C5 side measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -306,6 +307,32 @@ def main():
         want = O.distance_batch(ca[: oa[n_chk]], oa[: n_chk + 1].copy(), cb[: ob[n_chk]], ob[: n_chk + 1].copy(), costs)
         assert np.array_equal(check_dev[:n_chk], want), "GPU distances differ from the oracle"
 
+    # ---- side measurements of the other BASELINE configs (reduced sizes, N=1 only; full sizes: tools/bench_configs.py)
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs as BC
+            e3 = BC.c3(eng, 20000, reps=2); e4 = BC.c4(eng, reps=2); e5 = BC.c5(eng, 2_000_000, reps=2)
+            extras = {"c3_script_patch_roundtrip": {"pairs": e3["pairs"], "pairs_per_s_device": e3["device_pairs_per_s"],
+                                                    "gcups_device": e3["device_gcups"], "pairs_per_s_e2e_pageable": e3["e2e_pairs_per_s"],
+                                                    "roundtrip_ok": e3["roundtrip_ok"]},
+                      "c4_long_pair_50kb": {"gcups_device": e4["device_gcups"], "ms_device": e4["device_s"] * 1e3,
+                                            "forward_only_ms": e4["forward_only_device_s"] * 1e3, "n_ops": e4["n_ops"]},
+                      "c5_db_search_top10": {"records": e5["records"], "queries": e5["queries"], "gcups_device": e5["device_gcups"],
+                                             "ms_per_query_batch": e5["device_s"] * 1e3}}
+        except Exception as ex:                      # side measurements must never break the contract line
+            extras = {"error": repr(ex)}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if mode_used == 1 and args.pairs == tj.get("pairs"):
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this size" if traffic else None
+
     print(json.dumps({
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -314,7 +341,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-        "clocks": sampler.summary()}))
+        "clocks": sampler.summary(), "other_configs": extras}))
     if world > 1:
         dist.destroy_process_group()
 

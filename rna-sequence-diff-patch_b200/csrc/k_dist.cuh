@@ -1,15 +1,17 @@
 // k_dist.cuh — batched distance-only kernels (BASELINE config 2; also the scorer under wf_score).
 //
-// Systolic warp design: a pair's matrix is cut into strips of C columns; lane s of a group keeps
-// row i of strip s in C registers and works on row (t - s) at step t, so the only inter-lane
+// Systolic warp design: a pair's matrix is cut into strips of C columns; a lane keeps one row of
+// its strip in C registers and the lanes of a group run one row apart, so the only inter-lane
 // traffic is ONE __shfl_up per row (the strip's right-most cell).  Rows of the source string are
 // streamed from the packed words through L1; the destination codes of a strip are turned into
 // per-column selector registers once.  No shared-memory matrix, no HBM traffic besides the
-// packed inputs (2 or 4 bit / symbol) and 8 B / pair of output.
+// packed inputs (2 or 4 bit / symbol) and 8 B / pair of output.  Work arrives as warp tasks laid
+// out on a tape of 32*P lane slots (k_plan.cuh).
 //
 // Replaces (reference): the double loop of wagnerFisher SED:185-222 + min_cost SED:92-128,
 // read-out IR:439.
 #pragma once
+#include <type_traits>
 #include "k_plan.cuh"
 
 struct SeqView {
@@ -19,7 +21,7 @@ struct SeqView {
 };
 
 // =============================================================================================
-// Fast path: 2-bit codes (ACGU), scaled-int16 H' values, TWO pairs per register (hi/lo halves).
+// Fast path: 2-bit codes (ACGU), scaled-int16 values, TWO pairs per register (hi/lo halves).
 // Max form: N = -H' >= 0 and v = -w = ins + del - sub clamped to >= 0 (a substitution dearer than
 // delete+insert never wins, so the clamp leaves every value unchanged):
 //     N[i][j] = max(N[i][j-1], N[i-1][j], N[i-1][j-1] + v(a_i, b_j)),   D = m*del + n*ins - N.
@@ -36,37 +38,39 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
     if (threadIdx.x < 4) s_tab[threadIdx.x] = ic.rowtab4[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int n_warps = pv.totals[1];
-    uint32_t *scr = scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * scratch_stride;
+    const int n_tasks = pv.totals[1];
+    // two boundary columns per warp (ping-pong between passes)
+    uint32_t *scr = scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 * scratch_stride;
     const double inv_scale = 1.0 / (double)(1 << ic.scale_log2);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_tab);
 
     for (;;) {
         int W = 0;
         if (lane == 0) W = atomicAdd(pv.work_counter, 1);
         W = __shfl_sync(RSD_FULL, W, 0);
-        if (W >= n_warps) break;
-        const WarpTask tk = plan_decode(pv, W, lane);
-        int m = 0, nA = 0, nB = 0;
-        const uint32_t *awA = A.words, *awB = A.words, *bwA = B.words, *bwB = B.words;
-        if (tk.on) {
-            m = A.len[tk.pA]; nA = B.len[tk.pA]; nB = B.len[tk.pB];
-            awA = A.words + A.start[tk.pA]; awB = A.words + A.start[tk.pB];
-            bwA = B.words + B.start[tk.pA]; bwB = B.words + B.start[tk.pB];
+        if (W >= n_tasks) break;
+        const TapeTask tt = plan_decode(pv, W);
+        int ns = tt.ns, P = tt.P;
+        if (ns == 0) {                               // class of long pairs: one group, shape from the pair
+            const int p0 = pv.groups[tt.gfirst].x;
+            ns = (B.len[p0] + C - 1) / C; P = (ns + 31) >> 5;
         }
-        const int nmax = max(nA, nB);
-        const int ns = (nmax + C - 1) / C;
-        const int npass = tk.multi ? __shfl_sync(RSD_FULL, (ns + 31) >> 5, 0) : 1;
-        int resA = 0, resB = 0;
 
-        for (int pass = 0; pass < npass; ++pass) {
-            const int s = pass * 32 + tk.s0;
-            const bool strip_on = tk.on && s < ns;
-            const int col0 = s * C;
+        for (int pass = 0; pass < P; ++pass) {
+            const LaneSlot ls = tape_slot(pv, tt, ns, pass, lane);
+            int m = 0, nA = 0, nB = 0;
+            const uint32_t *awA = A.words, *awB = A.words, *bwA = B.words, *bwB = B.words;
+            if (ls.on) {
+                m = A.len[ls.pA]; nA = B.len[ls.pA]; nB = B.len[ls.pB];
+                awA = A.words + A.start[ls.pA]; awB = A.words + A.start[ls.pB];
+                bwA = B.words + B.start[ls.pA]; bwB = B.words + B.start[ls.pB];
+            }
+            const int col0 = ls.s * C;
             uint32_t sel[C];
 #pragma unroll
             for (int k = 0; k < C / 16; ++k) {
-                uint32_t xa = strip_on ? __ldg(bwA + (col0 >> 4) + k) : 0u;
-                uint32_t xb = strip_on ? __ldg(bwB + (col0 >> 4) + k) : 0u;
+                uint32_t xa = ls.on ? __ldg(bwA + (col0 >> 4) + k) : 0u;
+                uint32_t xb = ls.on ? __ldg(bwB + (col0 >> 4) + k) : 0u;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     uint32_t ca = (xa >> (2 * c)) & 3u, cb = (xb >> (2 * c)) & 3u;
@@ -78,17 +82,21 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
 #pragma unroll
             for (int c = 0; c < C; ++c) H[c] = 0u;
             uint32_t last = 0u, prev_recv = 0u, curA = 0u, curB = 0u;
-            const int steps = warp_max(strip_on ? m + tk.s0 : 0);
+            const int steps = warp_max(ls.on ? m + ls.sk : 0);
+            const bool has_in = __shfl_sync(RSD_FULL, (int)ls.from_scratch, 0) != 0;
+            const bool has_out = __shfl_sync(RSD_FULL, (int)ls.to_scratch, 31) != 0;
+            const uint32_t *scr_in = scr + ((pass & 1) ? scratch_stride : 0);
+            uint32_t *scr_out = scr + ((pass & 1) ? 0 : scratch_stride);
 
-            if (!tk.multi) {
-                // ---- single pass (n <= 32*C): the hot loop.  Rows are consumed in blocks of 16 steps so
-                // the source codes of a block sit in one register per pair: an unaligned 16-code window
-                // (funnel shift of two packed words), rotated so the current code is at bits [3:2] and can
-                // be OR-ed into the shared-memory address of the 4-entry row table.
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_tab);
-                const int mrow = strip_on ? m : 0;
-                const bool lead = tk.s0 == 0;
-                int i = -tk.s0;
+            // Rows are consumed in blocks of 16 steps so the source codes of a block sit in one register
+            // per pair: an unaligned 16-code window (funnel shift of two packed words), rotated so the
+            // current code is at bits [3:2] and can be OR-ed into the shared-memory address of the
+            // 4-entry row table.  Two copies of the loop: passes without a boundary hand-off (the common
+            // case) run the lean one.
+            const int mrow = ls.on ? m : 0;
+            auto run_rows = [&](auto handoff_tag) {
+                constexpr bool HANDOFF = decltype(handoff_tag)::value;
+                int i = -ls.sk;
 #pragma unroll 1
                 for (int t0 = 0; t0 < steps; t0 += 16) {
                     {
@@ -103,13 +111,15 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
 #pragma unroll 1
                     for (int k = 0; k < tend; ++k, ++i) {
                         uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
-                        if (lead) recv = 0u;
+                        if (ls.lead) recv = 0u;
+                        const bool row_on = (unsigned)i < (unsigned)mrow;
+                        if constexpr (HANDOFF) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
                         uint32_t ra, rb;
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sbase | (curA & 0xCu)));
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sbase | (curB & 0xCu)));
                         curA = __funnelshift_r(curA, curA, 2);
                         curB = __funnelshift_r(curB, curB, 2);
-                        if ((unsigned)i < (unsigned)mrow) {
+                        if (row_on) {
                             uint32_t left = recv, diag = prev_recv;
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
@@ -120,60 +130,29 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                                 left = H[c];
                             }
                             last = left; prev_recv = recv;
+                            if constexpr (HANDOFF) { if (ls.to_scratch) scr_out[i] = last; }
                         }
                     }
                 }
-            } else {
-            const bool wr_scr = tk.s0 == 31 && pass + 1 < npass;
-#pragma unroll 1
-            for (int t = 0; t < steps; ++t) {
-                uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
-                const int i = t - tk.s0;
-                const bool row_on = strip_on && (unsigned)i < (unsigned)m;
-                if (tk.s0 == 0) recv = (pass > 0 && row_on) ? scr[i] : 0u;
-                if (row_on) {
-                    if ((i & 15) == 0) { curA = __ldg(awA + (i >> 4)); curB = __ldg(awB + (i >> 4)); }
-                    const uint32_t ra = s_tab[curA & 3u]; curA >>= 2;
-                    const uint32_t rb = s_tab[curB & 3u]; curB >>= 2;
-                    uint32_t left = recv, diag = prev_recv;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint32_t v = prmt(ra, rb, sel[c]);
-                        const uint32_t x = add_fma(v, diag, one);
-                        diag = H[c];
-                        H[c] = max3u16x2(x, H[c], left);
-                        left = H[c];
-                    }
-                    last = left; prev_recv = recv;
-                    if (wr_scr) scr[i] = last;
-                }
-            }
-            }
-            if (strip_on) {
-                if (s == (nA - 1) / C) {
-                    const int cl = (nA - 1) - s * C;
+            };
+            if (has_in || has_out) run_rows(std::true_type{}); else run_rows(std::false_type{});
+            if (ls.on) {
+                if (ls.s == (nA - 1) / C) {
+                    const int cl = (nA - 1) - ls.s * C;
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    resA = (int)(v & 0xffffu);
+                    out[ls.pA] = (double)(m * ic.del + nA * ic.ins - (int)(v & 0xffffu)) * inv_scale;
                 }
-                if (s == (nB - 1) / C) {
-                    const int cl = (nB - 1) - s * C;
+                if (ls.hasB && ls.s == (nB - 1) / C) {
+                    const int cl = (nB - 1) - ls.s * C;
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    resB = (int)(v >> 16);
+                    out[ls.pB] = (double)(m * ic.del + nB * ic.ins - (int)(v >> 16)) * inv_scale;
                 }
             }
             __syncwarp();
-        }
-        if (tk.on) {
-            const int sA = tk.multi ? ((nA - 1) / C) & 31 : (nA - 1) / C;
-            if (tk.s0 == sA)
-                out[tk.pA] = (double)(m * ic.del + nA * ic.ins - resA) * inv_scale;
-            const int sB = tk.multi ? ((nB - 1) / C) & 31 : (nB - 1) / C;
-            if (tk.hasB && tk.s0 == sB)
-                out[tk.pB] = (double)(m * ic.del + nB * ic.ins - resB) * inv_scale;
         }
     }
 }
@@ -183,10 +162,6 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
 // of w from shared memory) or T = double (reference operation order, SED:95-109; borders are
 // products SED:159,177; no FMA contraction — every add/mul is an explicit _rn intrinsic).
 // =============================================================================================
-template <typename T> struct GenTab;
-template <> struct GenTab<int> { const IntCosts *c; };
-template <> struct GenTab<double> { const F64Costs *c; };
-
 template <typename T, int BITS, int C>
 __global__ void __launch_bounds__(128)
 k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
@@ -207,40 +182,39 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
     if constexpr (F64) { c_ins = fcp->ins; c_del = fcp->del; }
     else { c_ins = 0; c_del = 0; i_ins = icp->ins; i_del = icp->del; inv_scale = 1.0 / (double)(1 << icp->scale_log2); }
     const int lane = threadIdx.x & 31;
-    const int n_warps = pv.totals[1];
-    T *scr = scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * scratch_stride;
+    const int n_tasks = pv.totals[1];
+    T *scr = scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 * scratch_stride;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
 
     for (;;) {
         int W = 0;
         if (lane == 0) W = atomicAdd(pv.work_counter, 1);
         W = __shfl_sync(RSD_FULL, W, 0);
-        if (W >= n_warps) break;
-        const WarpTask tk = plan_decode(pv, W, lane);
-        int m = 0, n = 0;
-        const uint32_t *aw = A.words, *bw = B.words;
-        if (tk.on) {
-            m = A.len[tk.pA]; n = B.len[tk.pA];
-            aw = A.words + A.start[tk.pA]; bw = B.words + B.start[tk.pA];
+        if (W >= n_tasks) break;
+        const TapeTask tt = plan_decode(pv, W);
+        int ns = tt.ns, P = tt.P;
+        if (ns == 0) {
+            const int p0 = pv.groups[tt.gfirst].x;
+            ns = (B.len[p0] + C - 1) / C; P = (ns + 31) >> 5;
         }
-        const int ns = (n + C - 1) / C;
-        const int npass = tk.multi ? __shfl_sync(RSD_FULL, (ns + 31) >> 5, 0) : 1;
-        T res = 0;
 
-        for (int pass = 0; pass < npass; ++pass) {
-            const int s = pass * 32 + tk.s0;
-            const bool strip_on = tk.on && s < ns;
+        for (int pass = 0; pass < P; ++pass) {
+            const LaneSlot ls = tape_slot(pv, tt, ns, pass, lane);
+            int m = 0, n = 0;
+            const uint32_t *aw = A.words, *bw = B.words;
+            if (ls.on) {
+                m = A.len[ls.pA]; n = B.len[ls.pA];
+                aw = A.words + A.start[ls.pA]; bw = B.words + B.start[ls.pA];
+            }
+            const int s = ls.s;
             const int col0 = s * C;
-            int bc[C];                            // destination code of each column
+            int bc[C];                            // shared-memory byte address of each column's table column
 #pragma unroll
             for (int k = 0; k < C / PER; ++k) {
-                uint32_t x = strip_on ? __ldg(bw + col0 / PER + k) : 0u;
+                uint32_t x = ls.on ? __ldg(bw + col0 / PER + k) : 0u;
 #pragma unroll
-                for (int c = 0; c < PER; ++c) bc[k * PER + c] = (x >> (BITS * c)) & ((1u << BITS) - 1u);
-            }
-            {   // keep each column's shared-memory byte address; the row offset is added per row (one add per lookup)
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
-#pragma unroll
-                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase + (uint32_t)bc[c] * (uint32_t)sizeof(T));
+                for (int c = 0; c < PER; ++c)
+                    bc[k * PER + c] = (int)(sbase + ((x >> (BITS * c)) & ((1u << BITS) - 1u)) * (uint32_t)sizeof(T));
             }
             T H[C];
 #pragma unroll
@@ -250,19 +224,22 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
             }
             T last = 0, prev_recv = 0;
             uint32_t cur = 0u;
-            const int steps = warp_max(strip_on ? m + tk.s0 : 0);
-            const bool wr_scr = tk.multi && tk.s0 == 31 && pass + 1 < npass;
+            const int steps = warp_max(ls.on ? m + ls.sk : 0);
+            const bool has_in = __shfl_sync(RSD_FULL, (int)ls.from_scratch, 0) != 0;
+            const bool has_out = __shfl_sync(RSD_FULL, (int)ls.to_scratch, 31) != 0;
+            const T *scr_in = scr + ((pass & 1) ? scratch_stride : 0);
+            T *scr_out = scr + ((pass & 1) ? 0 : scratch_stride);
 
 #pragma unroll 1
             for (int t = 0; t < steps; ++t) {
                 T recv = __shfl_up_sync(RSD_FULL, last, 1);
-                const int i = t - tk.s0;
-                const bool row_on = strip_on && (unsigned)i < (unsigned)m;
-                if (tk.s0 == 0) {
-                    if (pass > 0) recv = row_on ? scr[i] : (T)0;
-                    else if constexpr (F64) recv = __dmul_rn((double)(i + 1), c_del);     // SED:177
+                const int i = t - ls.sk;
+                const bool row_on = ls.on && (unsigned)i < (unsigned)m;
+                if (ls.lead) {
+                    if constexpr (F64) recv = __dmul_rn((double)(i + 1), c_del);          // SED:177
                     else recv = 0;
                 }
+                if (has_in) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
                     const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)sizeof(T); cur >>= BITS;
@@ -281,7 +258,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                             const double c1 = __dadd_rn(H[c], c_del);      // SED:97
                             const double c2 = __dadd_rn(diag, w);          // SED:99
                             diag = H[c];
-                            H[c] = dmin2(dmin2(c0, c1), c2);                 // SED:106-107
+                            H[c] = dmin2(dmin2(c0, c1), c2);               // SED:106-107
                         } else {
                             const int t2 = addmin32(diag, w, H[c]);
                             diag = H[c];
@@ -290,22 +267,18 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                         left = H[c];
                     }
                     last = left; prev_recv = recv;
-                    if (wr_scr) scr[i] = last;
+                    if (has_out) { if (ls.to_scratch) scr_out[i] = last; }
                 }
             }
-            if (strip_on && s == (n - 1) / C) {
+            if (ls.on && s == (n - 1) / C) {
                 const int cl = (n - 1) - s * C;
+                T res = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
+                if constexpr (F64) out[ls.pA] = res;
+                else out[ls.pA] = (double)(res + m * i_del + n * i_ins) * inv_scale;
             }
             __syncwarp();
-        }
-        if (tk.on) {
-            const int sl = tk.multi ? ((n - 1) / C) & 31 : (n - 1) / C;
-            if (tk.s0 == sl) {
-                if constexpr (F64) out[tk.pA] = res;
-                else out[tk.pA] = (double)(res + m * i_del + n * i_ins) * inv_scale;
-            }
         }
     }
 }

@@ -1,44 +1,67 @@
 // k_plan.cuh — device-side work planning for the systolic warp kernels.
 //
 // A pair (m source symbols, n destination symbols) needs ns = ceil(n / C) lanes ("strips" of C
-// matrix columns held in registers).  Pairs are binned by (ns, m) with a counting sort so that
-// every warp is filled with groups of the same shape:
-//   * ns <= 32 : floor(32/ns) groups per warp, one pass;
-//   * ns  > 32 : one group per warp, ceil(ns/32) passes (class 33);
+// matrix columns held in registers).  Pairs are binned by (ns, m) with a counting sort.  The strips
+// of the G groups of one warp task are laid end to end on a *tape* of 32*P lane slots which the warp
+// walks in P passes; a group whose strips straddle a pass boundary hands its boundary column from
+// lane 31 of one pass to lane 0 of the next through a small per-warp scratch column.  (P, G) is
+// chosen per ns to minimise idle lanes: e.g. ns = 7 -> 9 groups on 2 passes (63 of 64 slots) instead
+// of 4 groups on one (28 of 32); ns = 47 -> 2 groups on 3 passes (94 of 96) instead of 1 on 2 (47/64).
 //   * "twin" bins put two pairs of identical (ns, m) into one group — the int16x2 kernels carry
-//     one pair in each half of every register.
+//     one pair in each half of every register;
+//   * pairs with more than RSD_NSQ_MAX strips form one class of single-group tasks.
 // Bins are numbered heaviest first so the persistent kernels hand out the long tasks first.
 #pragma once
 #include "rsd_common.cuh"
 
 #define RSD_MQ_MAX 2048                   // m is binned exactly below MQ-1, clamped above; MQ <= this
-#define RSD_NB_MAX (34 * RSD_MQ_MAX)      // classes ns = 0..33  (0 unused)
+#define RSD_NSQ_MAX 128                   // ns is binned exactly up to here; longer pairs share class NSQ_MAX+1
+#define RSD_NB_MAX ((RSD_NSQ_MAX + 2) * RSD_MQ_MAX)
 
 struct PlanView {
     int *pair_bin;        // [n_pairs] bin of each pair, -1 = trivial (m == 0 or n == 0)
     int *bin_cnt;         // [NB]
     int *bin_cursor;      // [NB]
     int *bin_group_off;   // [NB + 1] exclusive scan of groups per bin
-    int *bin_warp_off;    // [NB + 1] exclusive scan of warps per bin
+    int *bin_warp_off;    // [NB + 1] exclusive scan of warp tasks per bin
     int2 *groups;         // [n_pairs] {pair A, pair B or -1}
-    int *totals;          // {n_groups, n_warps}
+    int *totals;          // {n_groups, n_tasks}
     int *work_counter;    // persistent-kernel ticket
     int C;                // columns per lane
     int allow_twin;
     int MQ;               // row bins per class for this call: min(max_m + 2, RSD_MQ_MAX)
-    int NB;               // 34 * MQ
+    int NSC;              // strip classes for this call: min(max_ns, RSD_NSQ_MAX + 1); classes 1..NSC
+    int NB;               // NSC * MQ
 };
 
-__device__ __forceinline__ int plan_bin(int m, int n, int C, int MQ) {
-    int ns = (n + C - 1) / C;
-    int nsq = ns > 32 ? 33 : ns;
-    int mq = m < MQ - 1 ? m : MQ - 1;
-    return (33 - nsq) * MQ + (MQ - 1 - mq);
+__host__ __device__ __forceinline__ int plan_nsq(int ns) { return ns > RSD_NSQ_MAX ? RSD_NSQ_MAX + 1 : ns; }
+__device__ __forceinline__ int plan_bin(int m, int n, const PlanView &pv) {
+    const int nsq = plan_nsq((n + pv.C - 1) / pv.C);
+    const int mq = m < pv.MQ - 1 ? m : pv.MQ - 1;
+    return (pv.NSC - nsq) * pv.MQ + (pv.MQ - 1 - mq);
 }
-__device__ __forceinline__ int bin_nsq(int bin, int MQ) { return 33 - bin / MQ; }
-__device__ __forceinline__ int bin_mq(int bin, int MQ) { return MQ - 1 - bin % MQ; }
-__device__ __forceinline__ bool bin_twin(int bin, int allow_twin, int MQ) {
-    return allow_twin && bin_nsq(bin, MQ) <= 32 && bin_mq(bin, MQ) < MQ - 1;
+__device__ __forceinline__ int bin_nsq(int bin, const PlanView &pv) { return pv.NSC - bin / pv.MQ; }
+__device__ __forceinline__ int bin_mq(int bin, const PlanView &pv) { return pv.MQ - 1 - bin % pv.MQ; }
+__device__ __forceinline__ bool bin_twin(int bin, const PlanView &pv) {
+    return pv.allow_twin && bin_nsq(bin, pv) <= RSD_NSQ_MAX && bin_mq(bin, pv) < pv.MQ - 1;
+}
+
+// groups per task G and passes P for groups of ns strips: maximise the lane-slot utilisation
+// G*ns / (32*P).  Passes with a boundary hand-off run a slightly heavier row loop, so extra passes
+// are only taken when they buy at least 8 % more utilisation than the shortest layout.
+__host__ __device__ __forceinline__ void tape_shape(int nsq, int &P, int &G) {
+    if (nsq > RSD_NSQ_MAX) { P = 0; G = 1; return; }          // P depends on the pair: computed in the kernel
+    const int pmin = (nsq + 31) >> 5;
+    const int pmax = nsq <= 32 ? 4 : (pmin + 4 < 8 ? 8 : pmin + 4);
+    const int g0 = (32 * pmin) / nsq;
+    int bp = pmin, bg = g0;
+    for (int p = pmin + 1; p <= pmax; ++p) {
+        const int g = (32 * p) / nsq;
+        if ((long long)g * bp > (long long)bg * p) { bp = p; bg = g; }      // g/p > bg/bp
+    }
+    // utilisation ratio best/shortest = (bg/bp) / (g0/pmin) >= 1.08 ?
+    if ((long long)bg * pmin * 100 < (long long)g0 * bp * 108) { bp = pmin; bg = g0; }
+    P = bp; G = bg;
 }
 
 // trivial pairs are answered here: D = n*ins (m == 0) or m*del (n == 0) — one fp64 multiply,
@@ -53,12 +76,12 @@ __global__ void k_plan_count(const int32_t *__restrict__ a_len, const int32_t *_
         if (out) out[p] = m == 0 ? __dmul_rn((double)n, ins) : __dmul_rn((double)m, del);
         return;
     }
-    int bin = plan_bin(m, n, pv.C, pv.MQ);
+    int bin = plan_bin(m, n, pv);
     pv.pair_bin[p] = bin;
     atomicAdd(&pv.bin_cnt[bin], 1);
 }
 
-// one block of 1024 threads walks the bins in coalesced chunks of 1024; (groups, warps) are scanned
+// one block of 1024 threads walks the bins in coalesced chunks of 1024; (groups, tasks) are scanned
 // together as one 64-bit value with warp shuffles (three barriers per chunk)
 __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
     __shared__ unsigned long long s_warp[32];
@@ -68,13 +91,14 @@ __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
     for (int base = 0; base < pv.NB; base += 1024) {
         const int b = base + t;
         unsigned long long v = 0ull;
+        int c = 0;
         if (b < pv.NB) {
-            const int c = pv.bin_cnt[b];
+            c = pv.bin_cnt[b];
             if (c) {
-                const int groups = bin_twin(b, pv.allow_twin, pv.MQ) ? (c + 1) >> 1 : c;
-                const int nsq = bin_nsq(b, pv.MQ);
-                const int gpw = nsq > 32 ? 1 : 32 / nsq;
-                v = ((unsigned long long)groups << 32) | (unsigned)((groups + gpw - 1) / gpw);
+                const int groups = bin_twin(b, pv) ? (c + 1) >> 1 : c;
+                int P, G;
+                tape_shape(bin_nsq(b, pv), P, G);
+                v = ((unsigned long long)groups << 32) | (unsigned)((groups + G - 1) / G);
             }
         }
         unsigned long long inc = v;
@@ -101,9 +125,8 @@ __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
         if (b < pv.NB) {
             pv.bin_group_off[b] = (int)(excl >> 32); pv.bin_warp_off[b] = (int)(excl & 0xffffffffull);
             pv.bin_cursor[b] = 0;
-            const int c = pv.bin_cnt[b];
             // a twin bin with an odd count leaves its last group without a partner
-            if ((c & 1) && bin_twin(b, pv.allow_twin, pv.MQ)) pv.groups[(int)(excl >> 32) + (c >> 1)].y = -1;
+            if ((c & 1) && bin_twin(b, pv)) pv.groups[(int)(excl >> 32) + (c >> 1)].y = -1;
         }
         carry += s_total;
         __syncthreads();
@@ -122,42 +145,67 @@ __global__ void k_plan_fill(int64_t n_pairs, PlanView pv) {
     if (bin < 0) return;
     int r = atomicAdd(&pv.bin_cursor[bin], 1);
     int *g = reinterpret_cast<int *>(pv.groups);
-    if (bin_twin(bin, pv.allow_twin, pv.MQ)) g[2 * (pv.bin_group_off[bin] + (r >> 1)) + (r & 1)] = (int)p;
+    if (bin_twin(bin, pv)) g[2 * (pv.bin_group_off[bin] + (r >> 1)) + (r & 1)] = (int)p;
     else pv.groups[pv.bin_group_off[bin] + r] = make_int2((int)p, -1);
     pv.bin_cnt[bin] = 0;        // leave the counters zeroed for the next plan (nobody reads them after the scan)
 }
 
-// ---- what one warp task looks like, decoded by every lane ------------------------------------
-struct WarpTask {
-    int pA, pB;        // pair indices (pB == pA when the group has no twin); -1 when the lane idles
-    bool hasB;
-    int s0;            // strip index of this lane inside its group for pass 0 (== skew in rows)
-    bool multi;        // class 33: one group on the whole warp, several passes
-    bool on;           // lane belongs to a live group
+// ---- one warp task (warp-uniform part), decoded by every lane --------------------------------
+struct TapeTask {
+    int ns;            // strips per group; 0 = class of longer pairs (take it from the pair)
+    int P;             // passes (0 = from the pair)
+    int gfirst;        // index of the task's first group in pv.groups
+    int ng;            // groups in this task
 };
 
-__device__ __forceinline__ WarpTask plan_decode(const PlanView &pv, int W, int lane) {
+__device__ __forceinline__ TapeTask plan_decode(const PlanView &pv, int W) {
     int lo = 0, hi = pv.NB;                        // largest b with bin_warp_off[b] <= W
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (__ldg(&pv.bin_warp_off[mid]) <= W) lo = mid; else hi = mid;
     }
     const int b = lo;
-    const int nsq = bin_nsq(b, pv.MQ);
-    WarpTask t;
-    t.multi = nsq > 32;
-    const int gpw = t.multi ? 1 : 32 / nsq;
+    const int nsq = bin_nsq(b, pv);
+    int P, G;
+    tape_shape(nsq, P, G);
     const int gbase = __ldg(&pv.bin_group_off[b]);
     const int gcount = __ldg(&pv.bin_group_off[b + 1]) - gbase;
     const int wl = W - __ldg(&pv.bin_warp_off[b]);
-    const int g = t.multi ? 0 : lane / nsq;
-    t.s0 = t.multi ? lane : lane - g * nsq;
-    const int gi = wl * gpw + g;
-    t.on = g < gpw && gi < gcount;
-    t.pA = t.pB = -1; t.hasB = false;
-    if (t.on) {
-        int2 gp = pv.groups[gbase + gi];
-        t.pA = gp.x; t.hasB = gp.y >= 0; t.pB = t.hasB ? gp.y : gp.x;
-    }
+    TapeTask t;
+    t.ns = nsq > RSD_NSQ_MAX ? 0 : nsq;
+    t.P = P;
+    t.gfirst = gbase + wl * G;
+    t.ng = min(G, gcount - wl * G);
     return t;
+}
+
+// ---- what one lane does in one pass of a task -------------------------------------------------
+struct LaneSlot {
+    int pA, pB;        // pair indices (pB == pA when the group has no twin)
+    bool hasB;
+    bool on;           // the slot holds a strip
+    int s;             // strip index inside its group
+    int sk;            // row skew of this lane in this pass (lanes of one group run one row apart)
+    bool lead;         // s == 0: the matrix border is the left neighbour
+    bool from_scratch; // lane 0 continuing a group that started in the previous pass
+    bool to_scratch;   // lane 31 whose group continues in the next pass
+};
+
+__device__ __forceinline__ LaneSlot tape_slot(const PlanView &pv, const TapeTask &tt, int ns, int pass, int lane) {
+    LaneSlot ls;
+    const int q = pass * 32 + lane;
+    const int g = q / ns;
+    ls.s = q - g * ns;
+    ls.on = g < tt.ng;
+    const int q0 = max(g * ns, pass * 32);          // first slot of this group inside this pass
+    ls.sk = q - q0;
+    ls.lead = ls.s == 0;
+    ls.from_scratch = ls.on && lane == 0 && ls.s > 0;
+    ls.to_scratch = ls.on && lane == 31 && ls.s < ns - 1;
+    ls.pA = ls.pB = -1; ls.hasB = false;
+    if (ls.on) {
+        const int2 gp = pv.groups[tt.gfirst + g];
+        ls.pA = gp.x; ls.hasB = gp.y >= 0; ls.pB = ls.hasB ? gp.y : gp.x;
+    }
+    return ls;
 }

@@ -57,49 +57,51 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
     if constexpr (F64) { c_ins = fcp->ins; c_del = fcp->del; }
     else { i_ins = icp->ins; i_del = icp->del; inv_scale = 1.0 / (double)(1 << icp->scale_log2); }
     const int lane = threadIdx.x & 31;
-    const int n_warps = pv.totals[1];
-    const size_t wslot = (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * scratch_stride;
-    T *scr = (T *)scratch_v + wslot * (F64 ? 1 : 1);
+    const int n_tasks = pv.totals[1];
+    // per warp: two boundary columns (ping-pong between passes); fp64 mode keeps the step counts in a
+    // second slab behind all the cost columns
+    const size_t wslot = (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 * scratch_stride;
+    T *scr = (T *)scratch_v + wslot;
     int *scr_steps = nullptr;
-    if constexpr (F64) {
-        // fp64 mode keeps the step count beside the cost: second half of the scratch slab
-        scr_steps = (int *)((T *)scratch_v + (size_t)gridDim.x * (blockDim.x >> 5) * scratch_stride) + wslot;
-    }
+    if constexpr (F64)
+        scr_steps = (int *)((T *)scratch_v + (size_t)gridDim.x * (blockDim.x >> 5) * 2 * scratch_stride) + wslot;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
 
     for (;;) {
         int W = 0;
         if (lane == 0) W = atomicAdd(pv.work_counter, 1);
         W = __shfl_sync(RSD_FULL, W, 0);
-        if (W >= n_warps) break;
-        const WarpTask tk = plan_decode(pv, W, lane);
-        int m = 0, n = 0;
-        const uint32_t *aw = A.words, *bw = B.words;
-        uint32_t *dbase = sv.dirs;
-        if (tk.on) {
-            m = A.len[tk.pA]; n = B.len[tk.pA];
-            aw = A.words + A.start[tk.pA]; bw = B.words + B.start[tk.pA];
-            dbase = sv.dirs + sv.dir_off[tk.pA];
+        if (W >= n_tasks) break;
+        const TapeTask tt = plan_decode(pv, W);
+        int ns = tt.ns, P = tt.P;
+        if (ns == 0) {
+            const int p0 = pv.groups[tt.gfirst].x;
+            ns = (B.len[p0] + C - 1) / C; P = (ns + 31) >> 5;
         }
-        const int ns = (n + C - 1) / C;
         const int n_pad = ns * C;
-        const int npass = tk.multi ? __shfl_sync(RSD_FULL, (ns + 31) >> 5, 0) : 1;
-        T res = 0; int res_steps = 0;
 
-        for (int pass = 0; pass < npass; ++pass) {
-            const int s = pass * 32 + tk.s0;
-            const bool strip_on = tk.on && s < ns;
+        for (int pass = 0; pass < P; ++pass) {
+            const LaneSlot ls = tape_slot(pv, tt, ns, pass, lane);
+            int m = 0, n = 0;
+            const uint32_t *aw = A.words, *bw = B.words;
+            uint32_t *dbase = sv.dirs;
+            if (ls.on) {
+                m = A.len[ls.pA]; n = B.len[ls.pA];
+                aw = A.words + A.start[ls.pA]; bw = B.words + B.start[ls.pA];
+                dbase = sv.dirs + sv.dir_off[ls.pA];
+            }
+            const int s = ls.s;
             const int col0 = s * C;
             int bc[C];
 #pragma unroll
             for (int k = 0; k < C / PER; ++k) {
-                uint32_t x = strip_on ? __ldg(bw + col0 / PER + k) : 0u;
+                uint32_t x = ls.on ? __ldg(bw + col0 / PER + k) : 0u;
 #pragma unroll
-                for (int c = 0; c < PER; ++c) bc[k * PER + c] = (x >> (BITS * c)) & ((1u << BITS) - 1u);
-            }
-            if constexpr (!F64) {      // int path: keep the column's shared-memory byte address, add the row offset later
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
-#pragma unroll
-                for (int c = 0; c < C; ++c) bc[c] = (int)(sbase + ((uint32_t)bc[c] << 2));
+                for (int c = 0; c < PER; ++c) {
+                    const uint32_t code = (x >> (BITS * c)) & ((1u << BITS) - 1u);
+                    if constexpr (F64) bc[k * PER + c] = (int)code;
+                    else bc[k * PER + c] = (int)(sbase + (code << 2));      // shared byte address; row offset added per row
+                }
             }
             T H[C];
             int HS[F64 ? C : 1];
@@ -113,8 +115,10 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
             T last = 0, prev_recv = 0;
             int last_s = 0, prev_recv_s = 0;
             uint32_t cur = 0u;
-            const int steps = warp_max(strip_on ? m + tk.s0 : 0);
-            const bool wr_scr = tk.multi && tk.s0 == 31 && pass + 1 < npass;
+            const int steps = warp_max(ls.on ? m + ls.sk : 0);
+            const bool has_in = __shfl_sync(RSD_FULL, (int)ls.from_scratch, 0) != 0;
+            const bool has_out = __shfl_sync(RSD_FULL, (int)ls.to_scratch, 31) != 0;
+            const int off_in = (pass & 1) ? scratch_stride : 0, off_out = (pass & 1) ? 0 : scratch_stride;
             uint32_t *dcol = dbase + col0;
 
 #pragma unroll 1
@@ -122,14 +126,17 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                 T recv = __shfl_up_sync(RSD_FULL, last, 1);
                 int recv_s = 0;
                 if constexpr (F64) recv_s = __shfl_up_sync(RSD_FULL, last_s, 1);
-                const int i = t - tk.s0;
-                const bool row_on = strip_on && (unsigned)i < (unsigned)m;
-                if (tk.s0 == 0) {
-                    if (pass > 0) {
-                        recv = row_on ? scr[i] : (T)0;
-                        if constexpr (F64) recv_s = row_on ? scr_steps[i] : 0;
-                    } else if constexpr (F64) { recv = __dmul_rn((double)(i + 1), c_del); recv_s = i + 1; }
+                const int i = t - ls.sk;
+                const bool row_on = ls.on && (unsigned)i < (unsigned)m;
+                if (ls.lead) {
+                    if constexpr (F64) { recv = __dmul_rn((double)(i + 1), c_del); recv_s = i + 1; }
                     else recv = 0;
+                }
+                if (has_in) {
+                    if (ls.from_scratch && row_on) {
+                        recv = scr[off_in + i];
+                        if constexpr (F64) recv_s = scr_steps[off_in + i];
+                    }
                 }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
@@ -173,7 +180,9 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     }
                     last = left; prev_recv = recv;
                     if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
-                    if (wr_scr) { scr[i] = last; if constexpr (F64) scr_steps[i] = last_s; }
+                    if (has_out) {
+                        if (ls.to_scratch) { scr[off_out + i] = last; if constexpr (F64) scr_steps[off_out + i] = last_s; }
+                    }
                     if ((i & 15) == 15 || i == m - 1) {
                         const int sh = 2 * (15 - (i & 15));                  // partial last block: align as if 16 rows
                         uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * n_pad);
@@ -183,26 +192,21 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     }
                 }
             }
-            if (strip_on && s == (n - 1) / C) {
+            if (ls.on && s == (n - 1) / C) {
                 const int cl = (n - 1) - s * C;
+                T res = 0;
 #pragma unroll
-                for (int c = 0; c < C; ++c) if (c == cl) { res = H[c]; if constexpr (F64) res_steps = HS[c]; }
-            }
-            __syncwarp();
-        }
-        if (tk.on) {
-            const int sl = tk.multi ? ((n - 1) / C) & 31 : (n - 1) / C;
-            if (tk.s0 == sl) {
-                if constexpr (F64) sv.dist[tk.pA] = res;
+                for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
+                if constexpr (F64) sv.dist[ls.pA] = res;
                 else {
                     // undo the H' transform on the key, then split cost / steps
                     const long long key = (long long)res + (long long)m * (((long long)i_del << S) + 1)
                                           + (long long)n * (((long long)i_ins << S) + 1);
-                    sv.dist[tk.pA] = (double)(key >> S) * inv_scale;
+                    sv.dist[ls.pA] = (double)(key >> S) * inv_scale;
                 }
             }
+            __syncwarp();
         }
-        (void)res_steps;
     }
 }
 

@@ -275,11 +275,12 @@ extern "C" int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int
 // planning
 // ------------------------------------------------------------------------------------------------
 int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin,
-                       double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m) {
+                       double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n) {
     RSD_OK_OR_RETURN(plan_pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
     RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8)));
     pv.MQ = (int)std::min<int64_t>(std::max<int64_t>(max_m, 1) + 2, RSD_MQ_MAX);
-    pv.NB = 34 * pv.MQ;
+    pv.NSC = (int)std::min<int64_t>((std::max<int64_t>(max_n, 1) + C - 1) / C, RSD_NSQ_MAX + 1);
+    pv.NB = pv.NSC * pv.MQ;
     RSD_OK_OR_RETURN(plan_groups.ensure(sizeof(int2) * (size_t)n_pairs));
     int *bins = (int *)plan_bins.p;
     pv.pair_bin = (int *)plan_pair_bin.p;
@@ -345,39 +346,39 @@ int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const
     int blocks = 0;
     if (mi.mode == RSD_MODE_I16X2) {
         constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 1, d_out, st, pv, max_m));
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 1, d_out, st, pv, max_m, max_n));
         RSD_OK_OR_RETURN(persistent_grid(k_dist_twin16<C>, THREADS, sm_count, blocks));
-        const int stride = max_n > 32 * C ? (int)max_m : 0;
-        RSD_OK_OR_RETURN(scratch.ensure(sizeof(uint32_t) * (size_t)stride * blocks * wpb + 16));
+        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
+        RSD_OK_OR_RETURN(scratch.ensure(sizeof(uint32_t) * 2 * (size_t)stride * blocks * wpb + 16));
         if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
         k_dist_twin16<C><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)scratch.p, stride, 1u);
     } else if (mi.mode == RSD_MODE_I32) {
         constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m));
-        const int stride = max_n > 32 * C ? (int)max_m : 0;
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m, max_n));
+        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
         if (bits == 2) {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 2, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<int, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
         } else {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 4, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<int, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
         }
     } else {
         constexpr int C = 16;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m));
-        const int stride = max_n > 32 * C ? (int)max_m : 0;
+        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m, max_n));
+        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
         if (bits == 2) {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 2, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<double, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
         } else {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 4, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
             k_dist_gen<double, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
         }
@@ -710,8 +711,8 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
                else RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<true, 4, 16>, THREADS, sm_count, blocks)); }
     else { if (bits == 2) RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 2, 32>, THREADS, sm_count, blocks));
            else RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 4, 32>, THREADS, sm_count, blocks)); }
-    const int stride = max_n > 32 * C ? (int)max_m : 0;
-    RSD_OK_OR_RETURN(scratch.ensure((size_t)(f64 ? 12 : 4) * (size_t)stride * blocks * wpb + 64));
+    const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
+    RSD_OK_OR_RETURN(scratch.ensure((size_t)(f64 ? 12 : 4) * 2 * (size_t)stride * blocks * wpb + 64));
 
     const uint32_t *dA = (const uint32_t *)bufA.words.p, *dB = (const uint32_t *)bufB.words.p;
     const int64_t *sA = (const int64_t *)bufA.start.p, *sB = (const int64_t *)bufB.start.p;
@@ -722,7 +723,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         SeqView A{dA, sA + p0, lA + p0}, B{dB, sB + p0, lB + p0};
         PlanView pv;
         // trivial pairs (m == 0 or n == 0) get their distance from the planner and an all-INS / all-DEL script from the traceback
-        RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv, max_m));
+        RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv, max_m, max_n));
         ScriptView sv{(uint32_t *)dirs.p, (const int64_t *)misc.p + p0, (double *)out_f64.p + p0};
         if (f64) {
             if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);

@@ -98,7 +98,7 @@ struct rsd_ctx {
     int upload_seqs(SeqBufs &sb, const uint32_t *words, const int64_t *start, const int32_t *len, int64_t n,
                     int64_t n_words, cudaStream_t st);
     int make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin, double *d_out,
-                  cudaStream_t st, PlanView &pv, int64_t max_m);
+                  cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n);
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);

@@ -230,6 +230,8 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
             const T *scr_in = scr + ((pass & 1) ? scratch_stride : 0);
             T *scr_out = scr + ((pass & 1) ? 0 : scratch_stride);
 
+            auto run_rows = [&](auto handoff_tag) {          // two copies: passes without a hand-off run the lean one
+            constexpr bool HANDOFF = decltype(handoff_tag)::value;
 #pragma unroll 1
             for (int t = 0; t < steps; ++t) {
                 T recv = __shfl_up_sync(RSD_FULL, last, 1);
@@ -239,7 +241,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                     if constexpr (F64) recv = __dmul_rn((double)(i + 1), c_del);          // SED:177
                     else recv = 0;
                 }
-                if (has_in) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
+                if constexpr (HANDOFF) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
                     const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)sizeof(T); cur >>= BITS;
@@ -267,9 +269,11 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                         left = H[c];
                     }
                     last = left; prev_recv = recv;
-                    if (has_out) { if (ls.to_scratch) scr_out[i] = last; }
+                    if constexpr (HANDOFF) { if (ls.to_scratch) scr_out[i] = last; }
                 }
             }
+            };
+            if (has_in || has_out) run_rows(std::true_type{}); else run_rows(std::false_type{});
             if (ls.on && s == (n - 1) / C) {
                 const int cl = (n - 1) - s * C;
                 T res = 0;

@@ -121,6 +121,8 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
             const int off_in = (pass & 1) ? scratch_stride : 0, off_out = (pass & 1) ? 0 : scratch_stride;
             uint32_t *dcol = dbase + col0;
 
+            auto run_rows = [&](auto handoff_tag) {          // two copies: passes without a hand-off run the lean one
+            constexpr bool HANDOFF = decltype(handoff_tag)::value;
 #pragma unroll 1
             for (int t = 0; t < steps; ++t) {
                 T recv = __shfl_up_sync(RSD_FULL, last, 1);
@@ -132,7 +134,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     if constexpr (F64) { recv = __dmul_rn((double)(i + 1), c_del); recv_s = i + 1; }
                     else recv = 0;
                 }
-                if (has_in) {
+                if constexpr (HANDOFF) {
                     if (ls.from_scratch && row_on) {
                         recv = scr[off_in + i];
                         if constexpr (F64) recv_s = scr_steps[off_in + i];
@@ -180,7 +182,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     }
                     last = left; prev_recv = recv;
                     if constexpr (F64) { last_s = left_s; prev_recv_s = recv_s; }
-                    if (has_out) {
+                    if constexpr (HANDOFF) {
                         if (ls.to_scratch) { scr[off_out + i] = last; if constexpr (F64) scr_steps[off_out + i] = last_s; }
                     }
                     if ((i & 15) == 15 || i == m - 1) {
@@ -192,6 +194,8 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     }
                 }
             }
+            };
+            if (has_in || has_out) run_rows(std::true_type{}); else run_rows(std::false_type{});
             if (ls.on && s == (n - 1) / C) {
                 const int cl = (n - 1) - s * C;
                 T res = 0;

@@ -39,8 +39,8 @@ struct TopkState {
 // rowtab[q][i] = 8 bytes: v(query symbol i of q, compact symbol 0..6) = max(0, -w) <= 127; byte 7 (PAD) = 0
 __global__ void __launch_bounds__(128)
 k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_start,
-                const int32_t *__restrict__ db_len, int64_t rec0, int64_t n_rec, int db_bits, int64_t global_base,
-                const uint2 *__restrict__ rowtab, int QROWS, const int32_t *__restrict__ q_len, int n_queries,
+                const int32_t *__restrict__ db_len, int64_t rec0, int64_t n_rec, int db_bits,
+                const int64_t *__restrict__ perm, int64_t global_base, const uint2 *__restrict__ rowtab, int QROWS, const int32_t *__restrict__ q_len, int n_queries,
                 SearchTab tab, TopkState tk, double *__restrict__ all_scores, int64_t all_stride, uint32_t one) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2 *s_rows = reinterpret_cast<uint2 *>(smem_raw);                     // [n_queries][QROWS]
@@ -54,10 +54,16 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
     __syncthreads();
 
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t rA = rec0 + 2 * t, rB = rA + 1;
-    if (rA >= rec0 + n_rec) return;
-    const bool hasB = rB < rec0 + n_rec;
+    const int64_t rA0 = rec0 + 2 * t;
+    const bool live = rA0 < rec0 + n_rec;                     // dead threads idle through the loops (warp votes below)
+    const int64_t rA = live ? rA0 : rec0, rB = rA + 1;
+    const bool hasB = live && rB < rec0 + n_rec;
     const int nA = db_len[rA], nB = hasB ? db_len[rB] : nA;
+    // the database is stored sorted by length, so the records of a warp share (almost always) one
+    // length: columns left of the longest record are padding for every lane and are skipped, two at a time
+    int cskip = 32 - max(nA, nB);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cskip = min(cskip, __shfl_xor_sync(RSD_FULL, cskip, o));
     const uint32_t *wA = db_words + db_start[rA];
     const uint32_t *wB = hasB ? db_words + db_start[rB] : wA;
     const uint64_t lut = ((uint64_t)tab.compact_lut_hi << 32) | tab.compact_lut_lo;
@@ -92,31 +98,43 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
         for (int c = 0; c < 32; ++c) H[c] = 0u;
         const int m = s_qlen[q];
         const uint2 *rows = s_rows + (size_t)q * QROWS;
+#define RSD_SEARCH_CELL(c)                                                   \
+    {                                                                        \
+        const uint32_t v = prmt(r.x, r.y, sel[c]);                           \
+        const uint32_t x = add_fma(v, diag, one);                            \
+        diag = H[c];                                                         \
+        H[c] = max3u16x2(x, H[c], left);                                     \
+        left = H[c];                                                         \
+    }
 #pragma unroll 1
         for (int i = 0; i < m; ++i) {
             const uint2 r = rows[i];
             uint32_t left = 0u, diag = 0u;
+            // skipped columns hold the border value 0 and hand 0 to the first computed column
+            if (cskip < 2) { RSD_SEARCH_CELL(0) RSD_SEARCH_CELL(1) }
+            if (cskip < 4) { RSD_SEARCH_CELL(2) RSD_SEARCH_CELL(3) }
+            if (cskip < 6) { RSD_SEARCH_CELL(4) RSD_SEARCH_CELL(5) }
+            if (cskip < 8) { RSD_SEARCH_CELL(6) RSD_SEARCH_CELL(7) }
+            if (cskip < 10) { RSD_SEARCH_CELL(8) RSD_SEARCH_CELL(9) }
+            if (cskip < 12) { RSD_SEARCH_CELL(10) RSD_SEARCH_CELL(11) }
+            if (cskip < 14) { RSD_SEARCH_CELL(12) RSD_SEARCH_CELL(13) }
+            if (cskip < 16) { RSD_SEARCH_CELL(14) RSD_SEARCH_CELL(15) }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const uint32_t v = prmt(r.x, r.y, sel[c]);
-                const uint32_t x = add_fma(v, diag, one);
-                diag = H[c];
-                H[c] = max3u16x2(x, H[c], left);
-                left = H[c];
-            }
+            for (int c = 16; c < 32; ++c) RSD_SEARCH_CELL(c)
         }
+#undef RSD_SEARCH_CELL
         const int dA = m * tab.del + baseA - (int)(H[31] & 0xffffu);
         const int dB = m * tab.del + baseB - (int)(H[31] >> 16);
         // IR:440  score = 1 / (1 + cost)
         const double sA = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dA, tab.inv_scale)));
         const double sB = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dB, tab.inv_scale)));
-        if (all_scores) {
-            all_scores[(size_t)q * all_stride + rA] = sA;
-            if (hasB) all_scores[(size_t)q * all_stride + rB] = sB;
+        const long long gA = perm[rA], gB = perm[rB < rec0 + n_rec ? rB : rA];
+        if (all_scores && live) {
+            all_scores[(size_t)q * all_stride + (gA - global_base)] = sA;
+            if (hasB) all_scores[(size_t)q * all_stride + (gB - global_base)] = sB;
         }
-        if (tk.k > 0) {
+        if (tk.k > 0 && live) {
             const double ts = s_tau[q]; const long long ti = s_taui[q];
-            const long long gA = global_base + rA, gB = global_base + rB;
             if (sA > ts || (sA == ts && gA <= ti)) {
                 const int slot = atomicAdd(&tk.cand_n[q], 1);
                 if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
@@ -131,15 +149,15 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
 
 // General path: distances of one query against a range of records were produced by the systolic
 // distance kernels (any mode); turn them into scores, optional all_scores row, and candidates.
-__global__ void k_score_filter(const double *__restrict__ dist, int64_t rec0, int64_t n_rec, int64_t global_base, int q,
-                               TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
+__global__ void k_score_filter(const double *__restrict__ dist, int64_t rec0, int64_t n_rec, const int64_t *__restrict__ perm,
+                               int64_t global_base, int q, TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
     const double s = __ddiv_rn(1.0, __dadd_rn(1.0, dist[r]));
-    if (all_scores) all_scores[(size_t)q * all_stride + rec0 + r] = s;
+    const long long g = perm[rec0 + r];
+    if (all_scores) all_scores[(size_t)q * all_stride + (g - global_base)] = s;
     if (tk.k > 0) {
         const double ts = tk.tau_s[q]; const long long ti = tk.tau_i[q];
-        const long long g = global_base + rec0 + r;
         if (s > ts || (s == ts && g <= ti)) {
             const int slot = atomicAdd(&tk.cand_n[q], 1);
             if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = s; tk.cand_i[(size_t)q * tk.cap + slot] = g; }

@@ -854,11 +854,34 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
     if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
     if (bits == 2 && (symmask & ~0xFu)) return rsd_fail(RSD_EINVAL, "rsd_db_load: 2-bit packing with symbols outside ACGU");
     RSD_OK_OR_RETURN(c->ensure_device());
-    RSD_OK_OR_RETURN(c->upload_seqs(c->db, words, start, len, n_records, n_words, c->stream));
-    RSD_CUDA(cudaStreamSynchronize(c->stream));
-    c->db_n = n_records; c->db_base = global_index_base; c->db_nwords = n_words; c->db_bits = bits; c->db_symmask = symmask;
+    // Records are stored sorted by length (stable, so equal lengths keep collection order): the warps of
+    // the search kernel then hold records of one length and skip the padding columns.  perm[r] is the
+    // collection index of stored record r; every key and every all_scores row uses it.
+    const int per = 32 / bits;
     int32_t mx = 0;
-    for (int64_t i = 0; i < n_records; ++i) mx = std::max(mx, len[i]);
+    for (int64_t i = 0; i < n_records; ++i) { if (len[i] < 0) return rsd_fail(RSD_EINVAL, "rsd_db_load: negative length"); mx = std::max(mx, len[i]); }
+    std::vector<int64_t> cnt((size_t)mx + 2, 0);
+    for (int64_t i = 0; i < n_records; ++i) ++cnt[(size_t)len[i] + 1];
+    for (size_t l = 1; l < cnt.size(); ++l) cnt[l] += cnt[l - 1];
+    std::vector<int64_t> perm((size_t)std::max<int64_t>(n_records, 1)), s_start((size_t)std::max<int64_t>(n_records, 1));
+    std::vector<int32_t> s_len((size_t)std::max<int64_t>(n_records, 1));
+    for (int64_t i = 0; i < n_records; ++i) perm[(size_t)cnt[(size_t)len[i]]++] = i;
+    std::vector<uint32_t> s_words((size_t)n_words + 8, 0u);
+    int64_t w = 0;
+    for (int64_t r = 0; r < n_records; ++r) {
+        const int64_t i = perm[(size_t)r];
+        const int64_t nw = ((int64_t)len[i] + per - 1) / per;
+        if (start[i] < 0 || start[i] + nw > n_words) return rsd_fail(RSD_EINVAL, "rsd_db_load: record %lld lies outside the word buffer", (long long)i);
+        s_start[(size_t)r] = w; s_len[(size_t)r] = len[i];
+        memcpy(s_words.data() + w, words + start[i], sizeof(uint32_t) * (size_t)nw);
+        w += nw;
+    }
+    RSD_OK_OR_RETURN(c->upload_seqs(c->db, s_words.data(), s_start.data(), s_len.data(), n_records, std::max<int64_t>(w, 1), c->stream));
+    RSD_OK_OR_RETURN(c->db_perm.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n_records, 1)));
+    for (int64_t r = 0; r < n_records; ++r) perm[(size_t)r] += global_index_base;        // global index of stored record r
+    RSD_CUDA(cudaMemcpyAsync(c->db_perm.p, perm.data(), sizeof(int64_t) * (size_t)n_records, cudaMemcpyHostToDevice, c->stream));
+    RSD_CUDA(cudaStreamSynchronize(c->stream));
+    c->db_n = n_records; c->db_base = global_index_base; c->db_nwords = w; c->db_bits = bits; c->db_symmask = symmask;
     c->db_maxlen = mx;
     c->db_loaded = true;
     return RSD_OK;
@@ -866,7 +889,7 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
 
 extern "C" int rsd_db_free(rsd_ctx *c) {
     if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
-    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); }
+    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_perm.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); }
     c->db_loaded = false; c->db_n = 0;
     return RSD_OK;
 }
@@ -945,7 +968,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
             if (fast) {
                 const int64_t threads = (nr + 1) / 2;
                 const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
-                k_search_twin16<<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, db_base, rowtab, QROWS,
+                k_search_twin16<<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
                                                                                       q_len + q0, nq, tab, tk, alls, db_n, 1u);
                 launches += 1;
             } else {
@@ -959,7 +982,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
                                           dbl + r0, nr, max_qlen, db_maxlen, bits, symmask, force_mode, (double *)db_dist.p, &mode_unused, st);
                     timing = t_save;
                     if (rc) return rc;
-                    k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, db_base, q, tk, alls, db_n);
+                    k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, (const int64_t *)db_perm.p, db_base, q, tk, alls, db_n);
                     launches += 1;
                 }
             }

@@ -90,7 +90,7 @@ struct rsd_ctx {
     int db_bits = 0;
     uint32_t db_symmask = 0;
     bool db_loaded = false;
-    DevBuf db_dist, db_topi, db_tops, db_aux;
+    DevBuf db_dist, db_topi, db_tops, db_aux, db_perm;
 
     int ensure_device();
     int classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, int force_mode, ModeInfo &mi) const;
@@ -112,7 +112,7 @@ struct rsd_ctx {
         bufA.release(); bufB.release(); bufX.release(); bufQ.release(); db.release();
         DevBuf *all[] = {&out_f64, &scratch, &plan_pair_bin, &plan_bins, &plan_groups, &mat_vals, &mat_mask, &mat_ab,
                          &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
-                         &db_dist, &db_topi, &db_tops, &db_aux};
+                         &db_dist, &db_topi, &db_tops, &db_aux, &db_perm};
         for (DevBuf *b : all) b->release();
     }
 };

@@ -105,7 +105,15 @@ def cpu_baseline(ca, oa, cb, ob, costs, target_s=12.0, nthreads=0):
     return cells / dt * 1e-9, cores, f"first {n} pairs of the workload, C oracle port, {cores} threads", dt
 
 
+def _claim_stdout():
+    """Keep stdout for the single JSON line: libraries (NCCL prints its version banner there) get stderr."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -140,7 +148,7 @@ def main():
                 vals.append((g, dt))
         v = float(np.mean([g for g, _ in vals])) if vals else 0.0
         ms = float(np.mean([dt for _, dt in vals]) * 1e3) if vals else 0.0
-        print(json.dumps({
+        print(file=out, flush=True, *[json.dumps({
             "impl": "reference", "metric": "GCUPS", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -148,7 +156,7 @@ def main():
                              "note": "the reference is pure Python and cannot travel to the GPU box; this is the C "
                                      "restatement of its algorithm (oracle/wf_oracle.c), pinned to it by tests/golden"},
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})])
         return
 
     # ---------------------------------------------------------------- our arm
@@ -333,7 +341,7 @@ def main():
     roofline["traffic"] = traffic
     roofline["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this size" if traffic else None
 
-    print(json.dumps({
+    print(file=out, flush=True, *[json.dumps({
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {1: "s16x2", 2: "s32", 3: "f64"}[mode_used], "data": "synthetic",
@@ -341,7 +349,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-        "clocks": sampler.summary(), "other_configs": extras}))
+        "clocks": sampler.summary(), "other_configs": extras})])
     if world > 1:
         dist.destroy_process_group()
 

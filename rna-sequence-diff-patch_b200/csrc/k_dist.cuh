@@ -170,10 +170,15 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
     constexpr bool F64 = sizeof(T) == 8;
     constexpr int PER = 32 / BITS;               // symbols per packed word
     static_assert(C % PER == 0, "strip width must be a multiple of the packed word");
-    __shared__ T s_w[256];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-        if constexpr (F64) s_w[k] = fcp->sub[k >> 4][k & 15];
-        else s_w[k] = icp->w[k >> 4][k & 15];
+    // The 16x16 table is replicated once per bank (group): entry e of replica r lives at word-pair /
+    // word e*REP + r, so lane l always reads bank (pair) l % REP and the per-cell lookups of a warp are
+    // free of bank conflicts whatever symbols the lanes hold (one table would serialise 3-4 ways).
+    constexpr int REP = 128 / (int)sizeof(T);    // 16 replicas of 8-byte entries, 32 of 4-byte entries
+    __shared__ T s_w[256 * REP];
+    for (int k = threadIdx.x; k < 256 * REP; k += blockDim.x) {
+        const int e = k / REP;
+        if constexpr (F64) s_w[k] = fcp->sub[e >> 4][e & 15];
+        else s_w[k] = icp->w[e >> 4][e & 15];
     }
     __syncthreads();
     T c_ins, c_del;
@@ -214,7 +219,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                 uint32_t x = ls.on ? __ldg(bw + col0 / PER + k) : 0u;
 #pragma unroll
                 for (int c = 0; c < PER; ++c)
-                    bc[k * PER + c] = (int)(sbase + ((x >> (BITS * c)) & ((1u << BITS) - 1u)) * (uint32_t)sizeof(T));
+                    bc[k * PER + c] = (int)(sbase + (((x >> (BITS * c)) & ((1u << BITS) - 1u)) * REP + (lane % REP)) * (uint32_t)sizeof(T));
             }
             T H[C];
 #pragma unroll
@@ -244,7 +249,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                 if constexpr (HANDOFF) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
-                    const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)sizeof(T); cur >>= BITS;
+                    const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)(REP * sizeof(T)); cur >>= BITS;
                     T left = recv, diag = prev_recv;
                     if constexpr (F64) {
                         if (i == 0) diag = (s == 0) ? 0.0 : __dmul_rn((double)col0, c_ins);   // row-0 border

@@ -45,10 +45,13 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
     using T = typename std::conditional<F64, double, int>::type;
     constexpr int PER = 32 / BITS;
     static_assert(C % PER == 0 && C % 4 == 0, "strip width");
-    __shared__ T s_w[256];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-        if constexpr (F64) s_w[k] = fcp->sub[k >> 4][k & 15];
-        else s_w[k] = (int)(((unsigned)icp->w[k >> 4][k & 15] << S) - 1u);     // (w << S) - 1
+    // table replicated per bank (group) so the per-cell lookups never conflict (see k_dist_gen)
+    constexpr int REP = 128 / (int)sizeof(T);
+    __shared__ T s_w[256 * REP];
+    for (int k = threadIdx.x; k < 256 * REP; k += blockDim.x) {
+        const int e = k / REP;
+        if constexpr (F64) s_w[k] = fcp->sub[e >> 4][e & 15];
+        else s_w[k] = (int)(((unsigned)icp->w[e >> 4][e & 15] << S) - 1u);     // (w << S) - 1
     }
     __syncthreads();
     T c_ins = 0, c_del = 0;
@@ -99,8 +102,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
 #pragma unroll
                 for (int c = 0; c < PER; ++c) {
                     const uint32_t code = (x >> (BITS * c)) & ((1u << BITS) - 1u);
-                    if constexpr (F64) bc[k * PER + c] = (int)code;
-                    else bc[k * PER + c] = (int)(sbase + (code << 2));      // shared byte address; row offset added per row
+                    bc[k * PER + c] = (int)(sbase + (code * REP + (lane % REP)) * (uint32_t)sizeof(T));   // shared byte address; row offset added per row
                 }
             }
             T H[C];
@@ -142,7 +144,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                 }
                 if (row_on) {
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
-                    const int rowbase = (cur & ((1u << BITS) - 1u)) << 4; cur >>= BITS;
+                    const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)(REP * sizeof(T)); cur >>= BITS;
                     T left = recv, diag = prev_recv;
                     int left_s = recv_s, diag_s = prev_recv_s;
                     if constexpr (F64) {
@@ -152,8 +154,8 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         T w;
-                        if constexpr (F64) w = s_w[rowbase + bc[c]];
-                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] + ((uint32_t)rowbase << 2)));
+                        if constexpr (F64) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"((uint32_t)bc[c] + rowoff));
+                        else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(w) : "r"((uint32_t)bc[c] + rowoff));
                         if constexpr (F64) {
                             uint32_t code;
                             const double c0 = __dadd_rn(left, c_ins);

@@ -17,6 +17,7 @@
 //   every chunk by k_topk_fold, which also keeps the running top-k list.  The final order is a
 //   total order on (score, index), so the result does not depend on atomic ordering.
 #pragma once
+#include <type_traits>
 #include "k_dist.cuh"
 
 #define RSD_TOPK_MAX 128
@@ -92,58 +93,63 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
     }
     const int baseA = nA * tab.ins, baseB = nB * tab.ins;
 
-    for (int q = 0; q < n_queries; ++q) {
-        uint32_t H[32];
+    // One copy of the query loop per number of skipped padding columns (0, 2, .. 16): the column loop is
+    // fully unrolled from SKIP on, with no per-row tests.
+    auto run_queries = [&](auto skip_tag) {
+        constexpr int SKIP = decltype(skip_tag)::value;
+        for (int q = 0; q < n_queries; ++q) {
+            uint32_t H[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) H[c] = 0u;
-        const int m = s_qlen[q];
-        const uint2 *rows = s_rows + (size_t)q * QROWS;
-#define RSD_SEARCH_CELL(c)                                                   \
-    {                                                                        \
-        const uint32_t v = prmt(r.x, r.y, sel[c]);                           \
-        const uint32_t x = add_fma(v, diag, one);                            \
-        diag = H[c];                                                         \
-        H[c] = max3u16x2(x, H[c], left);                                     \
-        left = H[c];                                                         \
-    }
+            for (int c = 0; c < 32; ++c) H[c] = 0u;
+            const int m = s_qlen[q];
+            const uint2 *rows = s_rows + (size_t)q * QROWS;
 #pragma unroll 1
-        for (int i = 0; i < m; ++i) {
-            const uint2 r = rows[i];
-            uint32_t left = 0u, diag = 0u;
-            // skipped columns hold the border value 0 and hand 0 to the first computed column
-            if (cskip < 2) { RSD_SEARCH_CELL(0) RSD_SEARCH_CELL(1) }
-            if (cskip < 4) { RSD_SEARCH_CELL(2) RSD_SEARCH_CELL(3) }
-            if (cskip < 6) { RSD_SEARCH_CELL(4) RSD_SEARCH_CELL(5) }
-            if (cskip < 8) { RSD_SEARCH_CELL(6) RSD_SEARCH_CELL(7) }
-            if (cskip < 10) { RSD_SEARCH_CELL(8) RSD_SEARCH_CELL(9) }
-            if (cskip < 12) { RSD_SEARCH_CELL(10) RSD_SEARCH_CELL(11) }
-            if (cskip < 14) { RSD_SEARCH_CELL(12) RSD_SEARCH_CELL(13) }
-            if (cskip < 16) { RSD_SEARCH_CELL(14) RSD_SEARCH_CELL(15) }
+            for (int i = 0; i < m; ++i) {
+                const uint2 r = rows[i];
+                // skipped columns hold the border value 0 and hand 0 to the first computed column
+                uint32_t left = 0u, diag = 0u;
 #pragma unroll
-            for (int c = 16; c < 32; ++c) RSD_SEARCH_CELL(c)
-        }
-#undef RSD_SEARCH_CELL
-        const int dA = m * tab.del + baseA - (int)(H[31] & 0xffffu);
-        const int dB = m * tab.del + baseB - (int)(H[31] >> 16);
-        // IR:440  score = 1 / (1 + cost)
-        const double sA = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dA, tab.inv_scale)));
-        const double sB = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dB, tab.inv_scale)));
-        const long long gA = perm[rA], gB = perm[rB < rec0 + n_rec ? rB : rA];
-        if (all_scores && live) {
-            all_scores[(size_t)q * all_stride + (gA - global_base)] = sA;
-            if (hasB) all_scores[(size_t)q * all_stride + (gB - global_base)] = sB;
-        }
-        if (tk.k > 0 && live) {
-            const double ts = s_tau[q]; const long long ti = s_taui[q];
-            if (sA > ts || (sA == ts && gA <= ti)) {
-                const int slot = atomicAdd(&tk.cand_n[q], 1);
-                if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
+                for (int c = SKIP; c < 32; ++c) {
+                    const uint32_t v = prmt(r.x, r.y, sel[c]);
+                    const uint32_t x = add_fma(v, diag, one);
+                    diag = H[c];
+                    H[c] = max3u16x2(x, H[c], left);
+                    left = H[c];
+                }
             }
-            if (hasB && (sB > ts || (sB == ts && gB <= ti))) {
-                const int slot = atomicAdd(&tk.cand_n[q], 1);
-                if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sB; tk.cand_i[(size_t)q * tk.cap + slot] = gB; }
+            const int dA = m * tab.del + baseA - (int)(H[31] & 0xffffu);
+            const int dB = m * tab.del + baseB - (int)(H[31] >> 16);
+            // IR:440  score = 1 / (1 + cost)
+            const double sA = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dA, tab.inv_scale)));
+            const double sB = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn((double)dB, tab.inv_scale)));
+            const long long gA = perm[rA], gB = perm[rB < rec0 + n_rec ? rB : rA];
+            if (all_scores && live) {
+                all_scores[(size_t)q * all_stride + (gA - global_base)] = sA;
+                if (hasB) all_scores[(size_t)q * all_stride + (gB - global_base)] = sB;
+            }
+            if (tk.k > 0 && live) {
+                const double ts = s_tau[q]; const long long ti = s_taui[q];
+                if (sA > ts || (sA == ts && gA <= ti)) {
+                    const int slot = atomicAdd(&tk.cand_n[q], 1);
+                    if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
+                }
+                if (hasB && (sB > ts || (sB == ts && gB <= ti))) {
+                    const int slot = atomicAdd(&tk.cand_n[q], 1);
+                    if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sB; tk.cand_i[(size_t)q * tk.cap + slot] = gB; }
+                }
             }
         }
+    };
+    switch (min(cskip, 16) >> 1) {          // warp-uniform
+        case 0: run_queries(std::integral_constant<int, 0>{}); break;
+        case 1: run_queries(std::integral_constant<int, 2>{}); break;
+        case 2: run_queries(std::integral_constant<int, 4>{}); break;
+        case 3: run_queries(std::integral_constant<int, 6>{}); break;
+        case 4: run_queries(std::integral_constant<int, 8>{}); break;
+        case 5: run_queries(std::integral_constant<int, 10>{}); break;
+        case 6: run_queries(std::integral_constant<int, 12>{}); break;
+        case 7: run_queries(std::integral_constant<int, 14>{}); break;
+        default: run_queries(std::integral_constant<int, 16>{}); break;
     }
 }
 

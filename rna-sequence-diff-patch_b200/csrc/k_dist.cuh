@@ -108,7 +108,7 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                         curB = __funnelshift_l(__funnelshift_r(b0, b1, bit), __funnelshift_r(b0, b1, bit), 2);
                     }
                     const int tend = min(16, steps - t0);
-#pragma unroll 1
+#pragma unroll 2
                     for (int k = 0; k < tend; ++k, ++i) {
                         uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
                         if (ls.lead) recv = 0u;

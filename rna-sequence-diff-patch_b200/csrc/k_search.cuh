@@ -103,7 +103,7 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
             for (int c = 0; c < 32; ++c) H[c] = 0u;
             const int m = s_qlen[q];
             const uint2 *rows = s_rows + (size_t)q * QROWS;
-#pragma unroll 1
+#pragma unroll 2
             for (int i = 0; i < m; ++i) {
                 const uint2 r = rows[i];
                 // skipped columns hold the border value 0 and hand 0 to the first computed column

@@ -29,7 +29,8 @@ struct PlanView {
     int *work_counter;    // persistent-kernel ticket
     int C;                // columns per lane
     int allow_twin;
-    int MQ;               // row bins per class for this call: min(max_m + 2, RSD_MQ_MAX)
+    int m_shift;          // rows are binned as m >> m_shift: 0 (exact) when twins need equal m, coarser otherwise
+    int MQ;               // row bins per class for this call: min((max_m >> m_shift) + 2, RSD_MQ_MAX)
     int NSC;              // strip classes for this call: min(max_ns, RSD_NSQ_MAX + 1); classes 1..NSC
     int NB;               // NSC * MQ
 };
@@ -37,7 +38,8 @@ struct PlanView {
 __host__ __device__ __forceinline__ int plan_nsq(int ns) { return ns > RSD_NSQ_MAX ? RSD_NSQ_MAX + 1 : ns; }
 __device__ __forceinline__ int plan_bin(int m, int n, const PlanView &pv) {
     const int nsq = plan_nsq((n + pv.C - 1) / pv.C);
-    const int mq = m < pv.MQ - 1 ? m : pv.MQ - 1;
+    const int ms = m >> pv.m_shift;
+    const int mq = ms < pv.MQ - 1 ? ms : pv.MQ - 1;
     return (pv.NSC - nsq) * pv.MQ + (pv.MQ - 1 - mq);
 }
 __device__ __forceinline__ int bin_nsq(int bin, const PlanView &pv) { return pv.NSC - bin / pv.MQ; }

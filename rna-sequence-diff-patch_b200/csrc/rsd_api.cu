@@ -278,7 +278,12 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
                        double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n) {
     RSD_OK_OR_RETURN(plan_pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
     RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8)));
-    pv.MQ = (int)std::min<int64_t>(std::max<int64_t>(max_m, 1) + 2, RSD_MQ_MAX);
+    // twins need identical m; otherwise a task may mix pairs whose m differ a little (every lane keeps its
+    // own row count), so rows are binned ~3 % of max_m at a time and sparse shapes still fill their tapes
+    int lg = 0;
+    while (((int64_t)2 << lg) <= std::max<int64_t>(max_m, 1)) ++lg;              // floor(log2(max_m))
+    pv.m_shift = allow_twin ? 0 : std::min(std::max(lg - 5, 0), 6);
+    pv.MQ = (int)std::min<int64_t>((std::max<int64_t>(max_m, 1) >> pv.m_shift) + 2, RSD_MQ_MAX);
     pv.NSC = (int)std::min<int64_t>((std::max<int64_t>(max_n, 1) + C - 1) / C, RSD_NSQ_MAX + 1);
     pv.NB = pv.NSC * pv.MQ;
     RSD_OK_OR_RETURN(plan_groups.ensure(sizeof(int2) * (size_t)n_pairs));

@@ -1,6 +1,6 @@
 // k_long.cuh — one long pair (>= ~10 kb per side; BASELINE config 4: 50 kb x 50 kb with traceback).
 //
-// Block-tiled diagonal wavefront: the matrix is cut into column panels of 32*C columns; panel w is
+// Block-tiled diagonal wavefront: the matrix is cut into column panels of 32*C columns (C = 4); panel w is
 // owned by warp w (one warp per CTA so panels spread over all SMs) and, inside the panel, lane s
 // owns C columns in registers — the same systolic row pipeline as the batched kernels.  Panels run
 // concurrently as a second-level pipeline: the right-most column of panel w streams through a

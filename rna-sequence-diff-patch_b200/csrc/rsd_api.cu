@@ -1079,12 +1079,17 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     }
     cudaStream_t st = c->stream;
     RSD_OK_OR_RETURN(c->upload_costs(mi, st));
-    constexpr int C = 8;
+    // 4 columns per lane: the forward pass is latency-bound (one warp per panel, a dependent chain per
+    // row), so narrow panels = more panels in flight win until the panel pipeline lag dominates
+    // (measured at 50 kb: C=4 15.4 ms, C=8 22.8 ms, C=16 19.9 ms).
+    int C = 4;
+    if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) C = v; }
     const int n_panels = (int)((n + 32 * C - 1) / (32 * C));
     const int64_t n_pad = (int64_t)n_panels * 32 * C;
     int per_sm = 0;
-    if (f64) RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_long_fwd<true, C>, 32, 0));
-    else RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_long_fwd<false, C>, 32, 0));
+    const void *kfn = f64 ? (C == 4 ? (const void *)k_long_fwd<true, 4> : C == 16 ? (const void *)k_long_fwd<true, 16> : (const void *)k_long_fwd<true, 8>)
+                          : (C == 4 ? (const void *)k_long_fwd<false, 4> : C == 16 ? (const void *)k_long_fwd<false, 16> : (const void *)k_long_fwd<false, 8>);
+    RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32, 0));
     if ((int64_t)per_sm * c->sm_count < n_panels)
         return rsd_fail(RSD_ERANGE, "rsd_long_pair: %d column panels exceed the %d co-resident CTAs of this GPU (n too large for one wavefront launch)",
                         n_panels, per_sm * c->sm_count);
@@ -1111,8 +1116,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     const IntCosts *dic = c->d_ic; const F64Costs *dfc = c->d_fc;
     void *args[] = {&la, &dic, &dfc};
     if (c->timing) RSD_CUDA(cudaEventRecord(c->ev0, st));
-    if (f64) RSD_CUDA(cudaLaunchCooperativeKernel((void *)k_long_fwd<true, C>, dim3(n_panels), dim3(32), args, 0, st));
-    else RSD_CUDA(cudaLaunchCooperativeKernel((void *)k_long_fwd<false, C>, dim3(n_panels), dim3(32), args, 0, st));
+    RSD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(n_panels), dim3(32), args, 0, st));
     c->launches += 1;
     if (want_script) {
         RSD_OK_OR_RETURN(c->s_tmp.ensure((size_t)(m + n) + 64));

@@ -643,6 +643,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
                              uint8_t *op, int32_t *oi, int32_t *oj, int32_t *n_ops, double *dist, uint8_t *ok,
                              int *mode_out) {
     cudaStream_t st = stream;
+    last_ms_override = 0.0;
     const int64_t max_m = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, a_len[i]); return (int64_t)v; }();
     const int64_t max_n = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, b_len[i]); return (int64_t)v; }();
     if (max_ops < max_m + max_n && n_pairs > 0) {
@@ -910,7 +911,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     const uint32_t symmask = db_symmask | q_symmask;
     ModeInfo mi;
     RSD_OK_OR_RETURN(classify(symmask, max_qlen, db_maxlen, bits, force_mode == RSD_MODE_I16X2 ? 0 : force_mode, mi));
-    timed = false;
+    timed = false; last_ms_override = 0.0;
     // fast path applicability
     int nsym = 0; uint32_t syms_lo = 0, syms_hi = 0, lut_lo = 0x77777777u, lut_hi = 0x77777777u;
     bool w8 = true;
@@ -1067,7 +1068,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
         if (bound > 4.0e15) { if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_ERANGE, "rsd_long_pair: int64 key would overflow"); f64 = true; }
     } else if (force_mode == RSD_MODE_I32) return rsd_fail(RSD_EINVAL, "rsd_long_pair: integer mode not exact for these costs");
     if (mode_out) *mode_out = f64 ? RSD_MODE_F64 : RSD_MODE_I32;
-    c->timed = false;
+    c->timed = false; c->last_ms_override = 0.0;
     if (m == 0 || n == 0) {                     // border row / column only (SED:146-182): one product, all INS or all DEL
         *dist = m == 0 ? (double)n * c->ins : (double)m * c->del;
         if (want_script) {

@@ -12,16 +12,18 @@
 //   * pairs with more than RSD_NSQ_MAX strips form one class of single-group tasks.
 // Bins are numbered heaviest first so the persistent kernels hand out the long tasks first.
 #pragma once
+#include <cooperative_groups.h>
 #include "rsd_common.cuh"
 
 #define RSD_MQ_MAX 2048                   // m is binned exactly below MQ-1, clamped above; MQ <= this
 #define RSD_NSQ_MAX 128                   // ns is binned exactly up to here; longer pairs share class NSQ_MAX+1
 #define RSD_NB_MAX ((RSD_NSQ_MAX + 2) * RSD_MQ_MAX)
+#define RSD_PLAN_COPIES 8                 // privatised bin counters: the L2 serialises atomics per address
 
 struct PlanView {
     int *pair_bin;        // [n_pairs] bin of each pair, -1 = trivial (m == 0 or n == 0)
-    int *bin_cnt;         // [NB]
-    int *bin_cursor;      // [NB]
+    int *bin_cnt;         // [COPIES][NB_MAX] privatised counters (copy = warp index & 7)
+    int *bin_cursor;      // [COPIES][NB_MAX] per-copy cursors, preset to the copy's first rank inside its bin
     int *bin_group_off;   // [NB + 1] exclusive scan of groups per bin
     int *bin_warp_off;    // [NB + 1] exclusive scan of warp tasks per bin
     int2 *groups;         // [n_pairs] {pair A, pair B or -1}
@@ -33,6 +35,7 @@ struct PlanView {
     int MQ;               // row bins per class for this call: min((max_m >> m_shift) + 2, RSD_MQ_MAX)
     int NSC;              // strip classes for this call: min(max_ns, RSD_NSQ_MAX + 1); classes 1..NSC
     int NB;               // NSC * MQ
+    unsigned long long *dbg;
 };
 
 __host__ __device__ __forceinline__ int plan_nsq(int ns) { return ns > RSD_NSQ_MAX ? RSD_NSQ_MAX + 1 : ns; }
@@ -68,10 +71,8 @@ __host__ __device__ __forceinline__ void tape_shape(int nsq, int &P, int &G) {
 
 // trivial pairs are answered here: D = n*ins (m == 0) or m*del (n == 0) — one fp64 multiply,
 // like the reference's border rows (SED:159,177).
-__global__ void k_plan_count(const int32_t *__restrict__ a_len, const int32_t *__restrict__ b_len,
-                             int64_t n_pairs, PlanView pv, double ins, double del, double *out) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+__device__ __forceinline__ void plan_count_one(const int32_t *__restrict__ a_len, const int32_t *__restrict__ b_len, int64_t p,
+                                               const PlanView &pv, double ins, double del, double *out) {
     int m = a_len[p], n = b_len[p];
     if (m == 0 || n == 0) {
         pv.pair_bin[p] = -1;
@@ -80,12 +81,12 @@ __global__ void k_plan_count(const int32_t *__restrict__ a_len, const int32_t *_
     }
     int bin = plan_bin(m, n, pv);
     pv.pair_bin[p] = bin;
-    atomicAdd(&pv.bin_cnt[bin], 1);
+    atomicAdd(&pv.bin_cnt[(size_t)((threadIdx.x >> 5) & (RSD_PLAN_COPIES - 1)) * RSD_NB_MAX + bin], 1);
 }
 
 // one block of 1024 threads walks the bins in coalesced chunks of 1024; (groups, tasks) are scanned
 // together as one 64-bit value with warp shuffles (three barriers per chunk)
-__global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
+__device__ __forceinline__ void plan_scan_block(const PlanView &pv) {      // one block of 1024 threads
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -95,7 +96,13 @@ __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
         unsigned long long v = 0ull;
         int c = 0;
         if (b < pv.NB) {
-            c = pv.bin_cnt[b];
+#pragma unroll
+            for (int k = 0; k < RSD_PLAN_COPIES; ++k) {
+                const int ck = pv.bin_cnt[(size_t)k * RSD_NB_MAX + b];
+                pv.bin_cursor[(size_t)k * RSD_NB_MAX + b] = c;              // this copy's first rank inside the bin
+                if (ck) pv.bin_cnt[(size_t)k * RSD_NB_MAX + b] = 0;         // leave the counters zeroed for the next plan
+                c += ck;
+            }
             if (c) {
                 const int groups = bin_twin(b, pv) ? (c + 1) >> 1 : c;
                 int P, G;
@@ -126,7 +133,6 @@ __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
         const unsigned long long excl = carry + s_warp[wid] + (inc - v);
         if (b < pv.NB) {
             pv.bin_group_off[b] = (int)(excl >> 32); pv.bin_warp_off[b] = (int)(excl & 0xffffffffull);
-            pv.bin_cursor[b] = 0;
             // a twin bin with an odd count leaves its last group without a partner
             if ((c & 1) && bin_twin(b, pv)) pv.groups[(int)(excl >> 32) + (c >> 1)].y = -1;
         }
@@ -140,16 +146,36 @@ __global__ void __launch_bounds__(1024) k_plan_scan(PlanView pv) {
     }
 }
 
-__global__ void k_plan_fill(int64_t n_pairs, PlanView pv) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+__device__ __forceinline__ void plan_fill_one(int64_t p, const PlanView &pv) {
     int bin = pv.pair_bin[p];
     if (bin < 0) return;
-    int r = atomicAdd(&pv.bin_cursor[bin], 1);
+    int r = atomicAdd(&pv.bin_cursor[(size_t)((threadIdx.x >> 5) & (RSD_PLAN_COPIES - 1)) * RSD_NB_MAX + bin], 1);
     int *g = reinterpret_cast<int *>(pv.groups);
     if (bin_twin(bin, pv)) g[2 * (pv.bin_group_off[bin] + (r >> 1)) + (r & 1)] = (int)p;
     else pv.groups[pv.bin_group_off[bin] + r] = make_int2((int)p, -1);
-    pv.bin_cnt[bin] = 0;        // leave the counters zeroed for the next plan (nobody reads them after the scan)
+}
+
+// The whole plan as ONE cooperative launch (count -> grid sync -> scan by block 0 -> grid sync -> fill):
+// three dependent tiny kernels cost ~0.1 ms of launch latency per call, two grid syncs a few microseconds.
+__global__ void __launch_bounds__(1024) k_plan_all(const int32_t *__restrict__ a_len, const int32_t *__restrict__ b_len,
+                                                   int64_t n_pairs, PlanView pv, double ins, double del, double *out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
+        plan_count_one(a_len, b_len, p, pv, ins, del, out);
+    grid.sync();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (blockIdx.x == 0) plan_scan_block(pv);
+    grid.sync();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) plan_fill_one(p, pv);
+    if (pv.dbg) {                                   // RSD_TRACE: phase times
+        grid.sync();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3));
+        if (blockIdx.x == 0 && threadIdx.x == 0) { pv.dbg[0] = t1 - t0; pv.dbg[1] = t2 - t1; pv.dbg[2] = t3 - t2; }
+    }
 }
 
 // ---- one warp task (warp-uniform part), decoded by every lane --------------------------------

@@ -79,7 +79,10 @@ int rsd_ctx::ensure_device() {
     RSD_CUDA(cudaEventCreate(&ev0));
     RSD_CUDA(cudaEventCreate(&ev1));
     cur_ev0 = ev0; cur_ev1 = ev1;
-    for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { RSD_CUDA(cudaEventCreate(&ev_t0[k])); RSD_CUDA(cudaEventCreate(&ev_t1[k])); }
+    for (int k = 0; k < RSD_MAX_CHUNKS; ++k) {
+        RSD_CUDA(cudaEventCreate(&ev_t0[k])); RSD_CUDA(cudaEventCreate(&ev_t1[k]));
+        RSD_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
     RSD_CUDA(cudaMalloc(&d_ic, sizeof(IntCosts)));
     RSD_CUDA(cudaMalloc(&d_fc, sizeof(F64Costs)));
     pid = getpid();
@@ -97,7 +100,7 @@ extern "C" int rsd_destroy(rsd_ctx *c) {
         cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
         cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
         cudaEventDestroy(c->ev_sync);
-        for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { cudaEventDestroy(c->ev_chunk[k]); cudaEventDestroy(c->ev_t0[k]); cudaEventDestroy(c->ev_t1[k]); }
+        for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { cudaEventDestroy(c->ev_chunk[k]); cudaEventDestroy(c->ev_t0[k]); cudaEventDestroy(c->ev_t1[k]); cudaEventDestroy(c->ev_done[k]); }
     }
     delete c;
     return RSD_OK;
@@ -274,10 +277,23 @@ extern "C" int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int
 // ------------------------------------------------------------------------------------------------
 // planning
 // ------------------------------------------------------------------------------------------------
+template <typename K>
+static int persistent_grid(K kernel, int threads, int sm_count, int &blocks) {
+    static thread_local const void *cached_k[16]; static thread_local int cached_v[16]; static thread_local int n_cached = 0;
+    for (int i = 0; i < n_cached; ++i) if (cached_k[i] == (const void *)kernel) { blocks = cached_v[i] * sm_count; return RSD_OK; }
+    int per_sm = 0;
+    RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (n_cached < 16) { cached_k[n_cached] = (const void *)kernel; cached_v[n_cached] = per_sm; ++n_cached; }
+    blocks = per_sm * sm_count;
+    return RSD_OK;
+}
+
 int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin,
                        double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n) {
     RSD_OK_OR_RETURN(plan_pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8)));
+    const size_t plan_ints = (size_t)(2 * RSD_PLAN_COPIES) * RSD_NB_MAX + 2 * (RSD_NB_MAX + 1) + 16;
+    RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * plan_ints));
     // twins need identical m; otherwise a task may mix pairs whose m differ a little (every lane keeps its
     // own row count), so rows are binned ~3 % of max_m at a time and sparse shapes still fill their tapes
     int lg = 0;
@@ -291,26 +307,39 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     pv.pair_bin = (int *)plan_pair_bin.p;
     pv.bin_cnt = bins;
     // fixed array bases (independent of this call's NB) so the zeroed-counter invariant survives a change of NB
-    pv.bin_cursor = bins + (RSD_NB_MAX + 1);
-    pv.bin_group_off = bins + 2 * (RSD_NB_MAX + 1);
-    pv.bin_warp_off = bins + 3 * (RSD_NB_MAX + 1);
-    pv.totals = bins + 4 * (RSD_NB_MAX + 1);
+    pv.bin_cursor = bins + (size_t)RSD_PLAN_COPIES * RSD_NB_MAX;
+    pv.bin_group_off = bins + (size_t)(2 * RSD_PLAN_COPIES) * RSD_NB_MAX;
+    pv.bin_warp_off = pv.bin_group_off + (RSD_NB_MAX + 1);
+    pv.totals = pv.bin_warp_off + (RSD_NB_MAX + 1);
     pv.work_counter = pv.totals + 4;
     pv.groups = (int2 *)plan_groups.p;
     pv.C = C; pv.allow_twin = allow_twin;
-    // bin counters are left zeroed by k_plan_fill; cursors / ticket / odd-twin slots are reset by
-    // k_plan_scan — so a plan is three kernels and no memsets.  A call that failed between count and
+    pv.dbg = getenv("RSD_TRACE") ? (unsigned long long *)(pv.totals + 6) : nullptr;
+    // bin counters are zeroed again by the scan phase, which also resets cursors / ticket / odd-twin
+    // slots — so a plan is three kernels and no memsets.  A call that failed between count and
     // fill leaves them dirty: start clean then.
     if (plan_dirty) {
-        RSD_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 8), st));
+        RSD_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 16), st));
     }
     plan_dirty = true;
-    const int T = 256;
-    const unsigned G = (unsigned)((n_pairs + T - 1) / T);
-    k_plan_count<<<G, T, 0, st>>>(d_alen, d_blen, n_pairs, pv, ins, del, d_out);
-    k_plan_scan<<<1, 1024, 0, st>>>(pv);
-    k_plan_fill<<<G, T, 0, st>>>(n_pairs, pv);
-    launches += 3;
+    {
+        // one cooperative launch: every SM gets up to two 1024-thread blocks (grid-stride over the pairs)
+        int per_sm = 0;
+        RSD_OK_OR_RETURN(persistent_grid(k_plan_all, 1024, 1, per_sm));
+        const int64_t want = (n_pairs + 1023) / 1024;
+        const unsigned G = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count * std::min(per_sm, 2)));
+        double c_ins = ins, c_del = del;
+        void *args[] = {(void *)&d_alen, (void *)&d_blen, (void *)&n_pairs, (void *)&pv, (void *)&c_ins, (void *)&c_del, (void *)&d_out};
+        RSD_CUDA(cudaLaunchCooperativeKernel((const void *)k_plan_all, dim3(G), dim3(1024), args, 0, st));
+        launches += 1;
+        if (pv.dbg) {
+            unsigned long long d[3];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(d, pv.dbg, sizeof d, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[rsd trace] plan %lld pairs, %u blocks: count %.1f us, scan %.1f us, fill %.1f us\n", (long long)n_pairs, G,
+                    d[0] * 1e-3, d[1] * 1e-3, d[2] * 1e-3);
+        }
+    }
     RSD_CUDA(cudaGetLastError());
     plan_dirty = false;
     return RSD_OK;
@@ -319,18 +348,6 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
 // ------------------------------------------------------------------------------------------------
 // distance batch
 // ------------------------------------------------------------------------------------------------
-template <typename K>
-static int persistent_grid(K kernel, int threads, int sm_count, int &blocks) {
-    static thread_local const void *cached_k[16]; static thread_local int cached_v[16]; static thread_local int n_cached = 0;
-    for (int i = 0; i < n_cached; ++i) if (cached_k[i] == (const void *)kernel) { blocks = cached_v[i] * sm_count; return RSD_OK; }
-    int per_sm = 0;
-    RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (n_cached < 16) { cached_k[n_cached] = (const void *)kernel; cached_v[n_cached] = per_sm; ++n_cached; }
-    blocks = per_sm * sm_count;
-    return RSD_OK;
-}
-
 int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len,
                           const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len,
                           int64_t n_pairs, int64_t max_m, int64_t max_n, int bits, uint32_t symmask,
@@ -506,9 +523,13 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
                                  p1 - p0, max_m, max_n, bits, symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st);
         c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; c->costs_preloaded = false;
         if (rc) return rc;
-        RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, st));
+        // results go back on the copy stream so the next chunk's plan + kernel start right away
+        RSD_CUDA(cudaEventRecord(c->ev_done[k], st));
+        RSD_CUDA(cudaStreamWaitEvent(cp, c->ev_done[k], 0));
+        RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, cp));
     }
     t_comp = now();
+    RSD_CUDA(cudaStreamSynchronize(cp));
     RSD_CUDA(cudaStreamSynchronize(st));
     if (trace) fprintf(stderr, "[rsd trace] host ms: max_len %.3f, classify+costs %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
                        t_len - t_in, t_cost - t_len, t_copy - t_cost, t_comp - t_copy, now() - t_comp);

@@ -65,7 +65,7 @@ struct rsd_ctx {
     pid_t pid = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_sync = nullptr, ev_chunk[RSD_MAX_CHUNKS] = {}, ev_t0[RSD_MAX_CHUNKS] = {}, ev_t1[RSD_MAX_CHUNKS] = {};
+    cudaEvent_t ev_sync = nullptr, ev_chunk[RSD_MAX_CHUNKS] = {}, ev_t0[RSD_MAX_CHUNKS] = {}, ev_t1[RSD_MAX_CHUNKS] = {}, ev_done[RSD_MAX_CHUNKS] = {};
     cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr;
     double last_ms_override = 0.0;
     bool costs_preloaded = false;

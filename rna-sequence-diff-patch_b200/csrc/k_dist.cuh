@@ -237,7 +237,7 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
 
             auto run_rows = [&](auto handoff_tag) {          // two copies: passes without a hand-off run the lean one
             constexpr bool HANDOFF = decltype(handoff_tag)::value;
-#pragma unroll 1
+#pragma unroll (F64 ? 1 : 2)
             for (int t = 0; t < steps; ++t) {
                 T recv = __shfl_up_sync(RSD_FULL, last, 1);
                 const int i = t - ls.sk;

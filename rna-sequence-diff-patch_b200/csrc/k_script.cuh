@@ -35,8 +35,6 @@ struct ScriptView {
     double *dist;              // [n_pairs]
 };
 
-template <typename T> struct KeyCell { T v; };
-
 template <bool F64, int BITS, int C>
 __global__ void __launch_bounds__(128)
 k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
@@ -146,7 +144,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                     if (i % PER == 0) cur = __ldg(aw + i / PER);
                     const uint32_t rowoff = ((cur & ((1u << BITS) - 1u)) << 4) * (uint32_t)(REP * sizeof(T)); cur >>= BITS;
                     T left = recv, diag = prev_recv;
-                    int left_s = recv_s, diag_s = prev_recv_s;
+                    [[maybe_unused]] int left_s = recv_s, diag_s = prev_recv_s;
                     if constexpr (F64) {
                         if (i == 0) { diag = (s == 0) ? 0.0 : __dmul_rn((double)col0, c_ins); diag_s = col0; }
                         else if (s == 0) { diag = __dmul_rn((double)i, c_del); diag_s = i; }
@@ -266,7 +264,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs fa, int64_t n_pai
     const int64_t p = blockIdx.x;
     if (p >= n_pairs) return;
     __shared__ int s_ai[256], s_bj[256];
-    __shared__ int s_carry_i, s_carry_j, s_bad_src, s_bad_rt;
+    __shared__ int s_carry_i, s_carry_j, s_bad_src;
     const int tid = threadIdx.x;
     const int m = fa.A.len[p], n = fa.B.len[p];
     const int k_ops = fa.n_ops[p];
@@ -275,7 +273,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs fa, int64_t n_pai
     const bool do_patch = fa.patched != nullptr || fa.ok != nullptr || fa.err != nullptr;
     const int xlen = do_patch ? fa.X.len[p] : 0;
     const int64_t x0 = do_patch ? fa.X.start[p] : 0;
-    if (tid == 0) { s_carry_i = 0; s_carry_j = 0; s_bad_src = 0; s_bad_rt = 0; }
+    if (tid == 0) { s_carry_i = 0; s_carry_j = 0; s_bad_src = 0; }
     __syncthreads();
     for (int base = 0; base < k_ops; base += 256) {
         const int k = base + tid;

@@ -462,19 +462,30 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
     // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
     // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
     t_len = now();
-    // Three chunks whose sizes grow geometrically (1:2:4): the first copy is short, and because compute is slower
+    // Four chunks whose sizes grow geometrically (1:2:4:8): the first copy is short, and because compute is slower
     // than the copy no later chunk ever waits for its data.
     int n_chunks = 1;
     int64_t bounds[RSD_MAX_CHUNKS + 1];
     bounds[0] = 0;
     if (n_pairs >= (1 << 16)) {
-        n_chunks = 3;
+        n_chunks = 4;
         double wsum = 0, w = 1.0, acc = 0;
         for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= 2.0; }
         w = 1.0;
         for (int k = 0; k < n_chunks; ++k) { acc += w; w *= 2.0; bounds[k + 1] = (int64_t)((double)n_pairs * acc / wsum); }
     }
     bounds[n_chunks] = n_pairs;
+    // chunked copies need the sequences stored in pair order (what rsd_pack writes); when the chunk
+    // boundaries say otherwise (e.g. one sequence shared by many pairs) copy everything first
+    for (int k = 0; k < n_chunks && n_chunks > 1; ++k) {
+        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+        const int64_t a0 = a_start[p0], a1 = p1 < n_pairs ? a_start[p1] : a_nwords;
+        const int64_t b0 = b_start[p0], b1 = p1 < n_pairs ? b_start[p1] : b_nwords;
+        if (a0 < 0 || b0 < 0 || a1 < a0 || b1 < b0 || a1 > a_nwords || b1 > b_nwords || (k == 0 && (a0 != 0 || b0 != 0))) {
+            n_chunks = 1; bounds[1] = n_pairs;
+        }
+    }
+    const bool whole = n_chunks == 1;
     // costs go up first: a small pageable copy issued later would queue behind the big H2D copies on
     // the copy engine and stall the first kernel until every chunk has arrived.
     {
@@ -502,8 +513,8 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
-        const int64_t aw0 = a_start[p0], aw1 = p1 < n_pairs ? a_start[p1] : a_nwords;
-        const int64_t bw0 = b_start[p0], bw1 = p1 < n_pairs ? b_start[p1] : b_nwords;
+        const int64_t aw0 = whole ? 0 : a_start[p0], aw1 = (whole || p1 >= n_pairs) ? a_nwords : a_start[p1];
+        const int64_t bw0 = whole ? 0 : b_start[p0], bw1 = (whole || p1 >= n_pairs) ? b_nwords : b_start[p1];
         RSD_CUDA(cudaMemcpyAsync((uint32_t *)dA.words.p + aw0, a_words + aw0, sizeof(uint32_t) * (size_t)(aw1 - aw0), cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaMemcpyAsync((uint32_t *)dB.words.p + bw0, b_words + bw0, sizeof(uint32_t) * (size_t)(bw1 - bw0), cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaMemcpyAsync((int64_t *)dA.start.p + p0, a_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));

@@ -225,3 +225,25 @@ def test_wf_score_and_search_collection_g7(R, golden):
         assert [list(x) for x in IR.top_k(got["mean"], 6)] == golden["G7"][0]["top6"]
     finally:
         os.chdir(cwd)
+
+
+def test_shared_sequence_layout_falls_back_to_whole_copy(R, eng, golden):
+    """One query shared by every pair (all a_start equal): the chunked host copy must not be used."""
+    import ctypes as C
+    from rna_sequence_diff_patch_b200 import _lib
+    rng = np.random.default_rng(16)
+    n = 70000                                            # >= 65536 pairs -> chunking would kick in
+    b = rand_seqs(rng, n, 20, 40, "AGCU")
+    q = "ACGUACGGUUACGCAUUCGA"
+    B = R.pack(b); Q = R.pack([q])
+    a_start = np.zeros(n, np.int64); a_len = np.full(n, len(q), np.int32)
+    out = np.zeros(n)
+    eng.set_costs(golden["default_costs"])
+    mode = C.c_int()
+    _lib.check(R.load_library().rsd_distance_batch(
+        eng.ctx, _lib.ptr(Q.words, C.c_uint32), _lib.ptr(a_start, C.c_int64), _lib.ptr(a_len, C.c_int32), Q.words.shape[0],
+        _lib.ptr(B.words, C.c_uint32), _lib.ptr(B.start, C.c_int64), _lib.ptr(B.len, C.c_int32), B.words.shape[0],
+        n, len(q), 40, 2, 0xF, 0, _lib.ptr(out, C.c_double), C.byref(mode)))
+    sub = rng.choice(n, size=300, replace=False)
+    want = oracle_batch([q] * 300, [b[k] for k in sub], golden["default_costs"])
+    assert np.array_equal(out[sub], want)

@@ -98,7 +98,7 @@ int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int bits,
  * (0 = let the library scan a_len / b_len; an understated bound is an error the library cannot see).
  * force_mode: 0 = classify, or one of RSD_MODE_* (tests use it to cross-check the modes; forcing
  * an INT mode on costs that are not exactly representable fails with RSD_EINVAL).
- * Large batches are copied in four chunks on a copy stream while earlier chunks compute; that needs the
+ * Large batches are copied in five growing chunks on a copy stream while earlier chunks compute; that needs the
  * sequences stored in pair order (start[] non-decreasing, as rsd_pack writes them) — when the chunk
  * boundaries are not ordered the whole batch is copied first.
  * A context serialises its own work: do not overlap calls on one context from several streams. */

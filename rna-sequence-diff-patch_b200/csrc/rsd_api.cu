@@ -72,7 +72,11 @@ int rsd_ctx::ensure_device() {
                         prop.major, prop.minor);
     sm_count = prop.multiProcessorCount;
     RSD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    RSD_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     RSD_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RSD_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    RSD_CUDA(cudaEventCreateWithFlags(&ev_len, cudaEventDisableTiming));
+    RSD_CUDA(cudaEventCreateWithFlags(&ev_plans, cudaEventDisableTiming));
     RSD_CUDA(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
     for (int k = 0; k < RSD_MAX_CHUNKS; ++k) RSD_CUDA(cudaEventCreate(&ev_chunk[k]));
     RSD_CUDA(cudaEventCreate(&ev_begin));
@@ -98,8 +102,8 @@ extern "C" int rsd_destroy(rsd_ctx *c) {
         c->free_all();
         cudaFree(c->d_ic); cudaFree(c->d_fc);
         cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
-        cudaEventDestroy(c->ev_sync);
+        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->d2h_stream);
+        cudaEventDestroy(c->ev_sync); cudaEventDestroy(c->ev_len); cudaEventDestroy(c->ev_plans); cudaEventDestroy(c->ev_begin);
         for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { cudaEventDestroy(c->ev_chunk[k]); cudaEventDestroy(c->ev_t0[k]); cudaEventDestroy(c->ev_t1[k]); cudaEventDestroy(c->ev_done[k]); }
     }
     delete c;
@@ -291,9 +295,10 @@ static int persistent_grid(K kernel, int threads, int sm_count, int &blocks) {
 
 int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin,
                        double *d_out, cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n) {
-    RSD_OK_OR_RETURN(plan_pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
+    PlanSlot &sl = ps();
+    RSD_OK_OR_RETURN(sl.pair_bin.ensure(sizeof(int) * (size_t)n_pairs));
     const size_t plan_ints = (size_t)(2 * RSD_PLAN_COPIES) * RSD_NB_MAX + 2 * (RSD_NB_MAX + 1) + 16;
-    RSD_OK_OR_RETURN(plan_bins.ensure(sizeof(int) * plan_ints));
+    RSD_OK_OR_RETURN(sl.bins.ensure(sizeof(int) * plan_ints));
     // twins need identical m; otherwise a task may mix pairs whose m differ a little (every lane keeps its
     // own row count), so rows are binned ~3 % of max_m at a time and sparse shapes still fill their tapes
     int lg = 0;
@@ -302,9 +307,9 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     pv.MQ = (int)std::min<int64_t>((std::max<int64_t>(max_m, 1) >> pv.m_shift) + 2, RSD_MQ_MAX);
     pv.NSC = (int)std::min<int64_t>((std::max<int64_t>(max_n, 1) + C - 1) / C, RSD_NSQ_MAX + 1);
     pv.NB = pv.NSC * pv.MQ;
-    RSD_OK_OR_RETURN(plan_groups.ensure(sizeof(int2) * (size_t)n_pairs));
-    int *bins = (int *)plan_bins.p;
-    pv.pair_bin = (int *)plan_pair_bin.p;
+    RSD_OK_OR_RETURN(sl.groups.ensure(sizeof(int2) * (size_t)n_pairs));
+    int *bins = (int *)sl.bins.p;
+    pv.pair_bin = (int *)sl.pair_bin.p;
     pv.bin_cnt = bins;
     // fixed array bases (independent of this call's NB) so the zeroed-counter invariant survives a change of NB
     pv.bin_cursor = bins + (size_t)RSD_PLAN_COPIES * RSD_NB_MAX;
@@ -312,16 +317,16 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     pv.bin_warp_off = pv.bin_group_off + (RSD_NB_MAX + 1);
     pv.totals = pv.bin_warp_off + (RSD_NB_MAX + 1);
     pv.work_counter = pv.totals + 4;
-    pv.groups = (int2 *)plan_groups.p;
+    pv.groups = (int2 *)sl.groups.p;
     pv.C = C; pv.allow_twin = allow_twin;
     pv.dbg = getenv("RSD_TRACE") ? (unsigned long long *)(pv.totals + 6) : nullptr;
     // bin counters are zeroed again by the scan phase, which also resets cursors / ticket / odd-twin
     // slots — so a plan is three kernels and no memsets.  A call that failed between count and
     // fill leaves them dirty: start clean then.
-    if (plan_dirty) {
+    if (sl.dirty) {
         RSD_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)(4 * (RSD_NB_MAX + 1) + 16), st));
     }
-    plan_dirty = true;
+    sl.dirty = true;
     {
         // one cooperative launch: every SM gets up to two 1024-thread blocks (grid-stride over the pairs)
         int per_sm = 0;
@@ -341,74 +346,84 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
         }
     }
     RSD_CUDA(cudaGetLastError());
-    plan_dirty = false;
+    sl.dirty = false;
     return RSD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // distance batch
 // ------------------------------------------------------------------------------------------------
-int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len,
-                          const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len,
-                          int64_t n_pairs, int64_t max_m, int64_t max_n, int bits, uint32_t symmask,
-                          int force_mode, double *d_out, int *mode_out, cudaStream_t st) {
+int rsd_ctx::distance_plan(const int32_t *a_len, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
+                           int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st) {
     if (n_pairs < 0 || n_pairs > INT32_MAX) return rsd_fail(RSD_ERANGE, "rsd: n_pairs out of range");
     if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
     if (bits == 2 && (symmask & ~0xFu)) return rsd_fail(RSD_EINVAL, "rsd: 2-bit packing with symbols outside ACGU");
-    ModeInfo mi;
-    RSD_OK_OR_RETURN(classify(symmask, max_m, max_n, bits, force_mode, mi));
-    if (mode_out) *mode_out = mi.mode;
+    PlanSlot &sl = ps();
+    RSD_OK_OR_RETURN(classify(symmask, max_m, max_n, bits, force_mode, sl.mi));
+    if (mode_out) *mode_out = sl.mi.mode;
     timed = false; last_ms_override = 0.0;
+    sl.n_pairs = n_pairs;
     if (n_pairs == 0) return RSD_OK;
-    if (!costs_preloaded) RSD_OK_OR_RETURN(upload_costs(mi, st));
+    if (!costs_preloaded) RSD_OK_OR_RETURN(upload_costs(sl.mi, st));
+    const int C = sl.mi.mode == RSD_MODE_F64 ? 16 : 32;
+    return make_plan(a_len, b_len, n_pairs, C, sl.mi.mode == RSD_MODE_I16X2 ? 1 : 0, d_out, st, sl.pv, max_m, max_n);
+}
+
+int rsd_ctx::distance_launch(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len,
+                             const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len,
+                             int64_t max_m, int bits, double *d_out, cudaStream_t st) {
+    PlanSlot &sl = ps();
+    if (sl.n_pairs == 0) return RSD_OK;
+    const ModeInfo &mi = sl.mi;
+    const PlanView &pv = sl.pv;
     SeqView A{a_words, a_start, a_len}, B{b_words, b_start, b_len};
-    PlanView pv;
     constexpr int THREADS = 128;
     const int wpb = THREADS / 32;
     int blocks = 0;
+    const int stride = (int)max_m;           // two boundary columns of max_m rows per warp (tape passes)
     if (mi.mode == RSD_MODE_I16X2) {
-        constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 1, d_out, st, pv, max_m, max_n));
-        RSD_OK_OR_RETURN(persistent_grid(k_dist_twin16<C>, THREADS, sm_count, blocks));
-        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
-        RSD_OK_OR_RETURN(scratch.ensure(sizeof(uint32_t) * 2 * (size_t)stride * blocks * wpb + 16));
+        RSD_OK_OR_RETURN(persistent_grid(k_dist_twin16<32>, THREADS, sm_count, blocks));
+        RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(uint32_t) * 2 * (size_t)stride * blocks * wpb + 16));
         if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-        k_dist_twin16<C><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)scratch.p, stride, 1u);
+        k_dist_twin16<32><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)sl.scratch.p, stride, 1u);
     } else if (mi.mode == RSD_MODE_I32) {
-        constexpr int C = 32;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m, max_n));
-        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
         if (bits == 2) {
-            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 2, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 2, 32>, THREADS, sm_count, blocks));
+            RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-            k_dist_gen<int, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
+            k_dist_gen<int, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)sl.scratch.p, stride);
         } else {
-            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 4, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 4, 32>, THREADS, sm_count, blocks));
+            RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(int) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-            k_dist_gen<int, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)scratch.p, stride);
+            k_dist_gen<int, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (int *)sl.scratch.p, stride);
         }
     } else {
-        constexpr int C = 16;
-        RSD_OK_OR_RETURN(make_plan(a_len, b_len, n_pairs, C, 0, d_out, st, pv, max_m, max_n));
-        const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
         if (bits == 2) {
-            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 2, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 2, 16>, THREADS, sm_count, blocks));
+            RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-            k_dist_gen<double, 2, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
+            k_dist_gen<double, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)sl.scratch.p, stride);
         } else {
-            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 4, C>, THREADS, sm_count, blocks));
-            RSD_OK_OR_RETURN(scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
+            RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<double, 4, 16>, THREADS, sm_count, blocks));
+            RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(double) * 2 * (size_t)stride * blocks * wpb + 16));
             if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-            k_dist_gen<double, 4, C><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)scratch.p, stride);
+            k_dist_gen<double, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, d_out, (double *)sl.scratch.p, stride);
         }
     }
     if (timing) { RSD_CUDA(cudaEventRecord(cur_ev1, st)); timed = true; }
     launches += 1;
     RSD_CUDA(cudaGetLastError());
     return RSD_OK;
+}
+
+int rsd_ctx::distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len,
+                          const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len,
+                          int64_t n_pairs, int64_t max_m, int64_t max_n, int bits, uint32_t symmask,
+                          int force_mode, double *d_out, int *mode_out, cudaStream_t st) {
+    cur_slot = 0;
+    RSD_OK_OR_RETURN(distance_plan(a_len, b_len, n_pairs, max_m, max_n, bits, symmask, force_mode, d_out, mode_out, st));
+    return distance_launch(a_words, a_start, a_len, b_words, b_start, b_len, max_m, bits, d_out, st);
 }
 
 extern "C" int rsd_distance_batch_dev(rsd_ctx *c,
@@ -462,17 +477,20 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
     // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
     // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
     t_len = now();
-    // Four chunks whose sizes grow geometrically (1:2:4:8): the first copy is short, and because compute is slower
-    // than the copy no later chunk ever waits for its data.
+    // Chunk sizes grow geometrically so the first copy is short; the growth stays below the compute/copy time
+    // ratio so that no later chunk waits for its data.
     int n_chunks = 1;
     int64_t bounds[RSD_MAX_CHUNKS + 1];
     bounds[0] = 0;
     if (n_pairs >= (1 << 16)) {
-        n_chunks = 4;
+        n_chunks = 5;
+        double ratio = 1.5;
+        if (const char *e = getenv("RSD_CHUNKS")) n_chunks = std::min(std::max(atoi(e), 1), RSD_MAX_CHUNKS);
+        if (const char *e = getenv("RSD_CHUNK_RATIO")) ratio = std::max(atof(e), 1.0);
         double wsum = 0, w = 1.0, acc = 0;
-        for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= 2.0; }
+        for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= ratio; }
         w = 1.0;
-        for (int k = 0; k < n_chunks; ++k) { acc += w; w *= 2.0; bounds[k + 1] = (int64_t)((double)n_pairs * acc / wsum); }
+        for (int k = 0; k < n_chunks; ++k) { acc += w; w *= ratio; bounds[k + 1] = (int64_t)((double)n_pairs * acc / wsum); }
     }
     bounds[n_chunks] = n_pairs;
     // chunked copies need the sequences stored in pair order (what rsd_pack writes); when the chunk
@@ -510,6 +528,11 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
     RSD_CUDA(cudaEventRecord(c->ev_begin, cp));
     const bool timing = c->timing;
     float kernel_ms = 0.f;
+    // Lengths of the whole batch go first (8 bytes per pair): every chunk is planned from them right away, so
+    // afterwards the compute streams hold nothing but the chunk kernels.
+    RSD_CUDA(cudaMemcpyAsync(dA.len.p, a_len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
+    RSD_CUDA(cudaMemcpyAsync(dB.len.p, b_len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
+    RSD_CUDA(cudaEventRecord(c->ev_len, cp));
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
@@ -519,28 +542,42 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
         RSD_CUDA(cudaMemcpyAsync((uint32_t *)dB.words.p + bw0, b_words + bw0, sizeof(uint32_t) * (size_t)(bw1 - bw0), cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaMemcpyAsync((int64_t *)dA.start.p + p0, a_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaMemcpyAsync((int64_t *)dB.start.p + p0, b_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
-        RSD_CUDA(cudaMemcpyAsync((int32_t *)dA.len.p + p0, a_len + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
-        RSD_CUDA(cudaMemcpyAsync((int32_t *)dB.len.p + p0, b_len + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
     }
     t_copy = now();
+    struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
+    c->costs_preloaded = true;
+    RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
-        RSD_CUDA(cudaStreamWaitEvent(st, c->ev_chunk[k], 0));
-        c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k]; c->costs_preloaded = true;
-        int rc = c->distance_dev((const uint32_t *)dA.words.p, (const int64_t *)dA.start.p + p0, (const int32_t *)dA.len.p + p0,
-                                 (const uint32_t *)dB.words.p, (const int64_t *)dB.start.p + p0, (const int32_t *)dB.len.p + p0,
-                                 p1 - p0, max_m, max_n, bits, symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st);
-        c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; c->costs_preloaded = false;
-        if (rc) return rc;
-        // results go back on the copy stream so the next chunk's plan + kernel start right away
-        RSD_CUDA(cudaEventRecord(c->ev_done[k], st));
-        RSD_CUDA(cudaStreamWaitEvent(cp, c->ev_done[k], 0));
-        RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, cp));
+        c->cur_slot = k;
+        RSD_OK_OR_RETURN(c->distance_plan((const int32_t *)dA.len.p + p0, (const int32_t *)dB.len.p + p0, p1 - p0, max_m, max_n, bits,
+                                          symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st));
+    }
+    RSD_CUDA(cudaEventRecord(c->ev_plans, st));
+    RSD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_plans, 0));
+    // chunk kernels alternate between two streams: the next chunk's blocks move in while the last tasks of the
+    // previous chunk drain, so a chunk boundary costs no idle SMs
+    for (int k = 0; k < n_chunks; ++k) {
+        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+        if (p1 <= p0) continue;
+        cudaStream_t sk = (k & 1) ? c->stream2 : st;
+        c->cur_slot = k;
+        RSD_CUDA(cudaStreamWaitEvent(sk, c->ev_chunk[k], 0));
+        c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k];
+        RSD_OK_OR_RETURN(c->distance_launch((const uint32_t *)dA.words.p, (const int64_t *)dA.start.p + p0, (const int32_t *)dA.len.p + p0,
+                                            (const uint32_t *)dB.words.p, (const int64_t *)dB.start.p + p0, (const int32_t *)dB.len.p + p0,
+                                            max_m, bits, (double *)c->out_f64.p + p0, sk));
+        // results go back on their own stream, behind nothing but the chunk's kernel
+        RSD_CUDA(cudaEventRecord(c->ev_done[k], sk));
+        RSD_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
+        RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
     t_comp = now();
+    RSD_CUDA(cudaStreamSynchronize(c->d2h_stream));
     RSD_CUDA(cudaStreamSynchronize(cp));
+    RSD_CUDA(cudaStreamSynchronize(c->stream2));
     RSD_CUDA(cudaStreamSynchronize(st));
     if (trace) fprintf(stderr, "[rsd trace] host ms: max_len %.3f, classify+costs %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
                        t_len - t_in, t_cost - t_len, t_copy - t_cost, t_comp - t_copy, now() - t_comp);
@@ -603,22 +640,22 @@ extern "C" int rsd_ubench(rsd_ctx *c, int which, double *ops_per_s) {
     if (!c || !ops_per_s) return rsd_fail(RSD_EINVAL, "rsd_ubench: NULL argument");
     RSD_OK_OR_RETURN(c->ensure_device());
     cudaStream_t st = c->stream;
-    RSD_OK_OR_RETURN(c->scratch.ensure(64));
+    RSD_OK_OR_RETURN(c->ps().scratch.ensure(64));
     const int threads = 256, blocks = c->sm_count * 8, iters = 2000;
     const uint32_t y = 0x00010003u, z = 0x00070002u;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         RSD_CUDA(cudaEventRecord(c->ev0, st));
         switch (which) {
-            case 0: k_ubench_u32<0><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 1: k_ubench_u32<1><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 2: k_ubench_u32<2><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 3: k_ubench_u32<3><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 4: k_ubench_f64<<<blocks, threads, 0, st>>>(iters, 1.5, (double *)c->scratch.p); break;
-            case 5: k_ubench_u32<5><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 6: k_ubench_u32<6><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 7: k_ubench_mix<<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
-            case 8: k_ubench_u32<8><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->scratch.p); break;
+            case 0: k_ubench_u32<0><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 1: k_ubench_u32<1><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 2: k_ubench_u32<2><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 3: k_ubench_u32<3><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 4: k_ubench_f64<<<blocks, threads, 0, st>>>(iters, 1.5, (double *)c->ps().scratch.p); break;
+            case 5: k_ubench_u32<5><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 6: k_ubench_u32<6><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 7: k_ubench_mix<<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 8: k_ubench_u32<8><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
             default: return rsd_fail(RSD_EINVAL, "rsd_ubench: unknown kind %d", which);
         }
         RSD_CUDA(cudaEventRecord(c->ev1, st));
@@ -750,7 +787,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
     else { if (bits == 2) RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 2, 32>, THREADS, sm_count, blocks));
            else RSD_OK_OR_RETURN(persistent_grid(k_script_fwd<false, 4, 32>, THREADS, sm_count, blocks)); }
     const int stride = (int)max_m;       // two boundary columns of max_m rows per warp (tape passes)
-    RSD_OK_OR_RETURN(scratch.ensure((size_t)(f64 ? 12 : 4) * 2 * (size_t)stride * blocks * wpb + 64));
+    RSD_OK_OR_RETURN(ps().scratch.ensure((size_t)(f64 ? 12 : 4) * 2 * (size_t)stride * blocks * wpb + 64));
 
     const uint32_t *dA = (const uint32_t *)bufA.words.p, *dB = (const uint32_t *)bufB.words.p;
     const int64_t *sA = (const int64_t *)bufA.start.p, *sB = (const int64_t *)bufB.start.p;
@@ -764,11 +801,11 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         RSD_OK_OR_RETURN(make_plan(lA + p0, lB + p0, np, C, 0, (double *)out_f64.p + p0, st, pv, max_m, max_n));
         ScriptView sv{(uint32_t *)dirs.p, (const int64_t *)misc.p + p0, (double *)out_f64.p + p0};
         if (f64) {
-            if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
-            else k_script_fwd<true, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
+            if (bits == 2) k_script_fwd<true, 2, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, ps().scratch.p, stride, -1);
+            else k_script_fwd<true, 4, 16><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, ps().scratch.p, stride, -1);
         } else {
-            if (bits == 2) k_script_fwd<false, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
-            else k_script_fwd<false, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, scratch.p, stride, -1);
+            if (bits == 2) k_script_fwd<false, 2, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, ps().scratch.p, stride, -1);
+            else k_script_fwd<false, 4, 32><<<blocks, THREADS, 0, st>>>(pv, A, B, d_ic, d_fc, sv, S, ps().scratch.p, stride, -1);
         }
         k_traceback<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(lA + p0, lB + p0, np, (const uint32_t *)dirs.p,
                                                                (const int64_t *)misc.p + p0, C, (uint8_t *)s_tmp.p, max_ops,
@@ -1128,7 +1165,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
                         n_panels, per_sm * c->sm_count);
     const size_t dir_words = (size_t)((m + 15) / 16) * (size_t)n_pad;
     RSD_OK_OR_RETURN(c->dirs.ensure(dir_words * 4 + 64));
-    RSD_OK_OR_RETURN(c->scratch.ensure((size_t)n_panels * (size_t)m * 12 + (size_t)n_panels * 4 + 256));
+    RSD_OK_OR_RETURN(c->ps().scratch.ensure((size_t)n_panels * (size_t)m * 12 + (size_t)n_panels * 4 + 256));
     RSD_OK_OR_RETURN(c->mat_ab.ensure((size_t)m + n + 64));
     RSD_OK_OR_RETURN(c->out_f64.ensure(64));
     uint8_t *da = (uint8_t *)c->mat_ab.p, *db = da + ((m + 15) / 16) * 16;
@@ -1137,9 +1174,9 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     LongArgs la{};
     la.a = da; la.m = (int)m; la.b = db; la.n = (int)n; la.n_panels = n_panels; la.n_pad = (int)n_pad;
     la.dirs = (uint32_t *)c->dirs.p;
-    la.bound = c->scratch.p;
-    la.bound_steps = (int *)((unsigned char *)c->scratch.p + (size_t)n_panels * (size_t)m * 8);
-    la.progress = (int *)((unsigned char *)c->scratch.p + (size_t)n_panels * (size_t)m * 12);
+    la.bound = c->ps().scratch.p;
+    la.bound_steps = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)m * 8);
+    la.progress = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)m * 12);
     la.dist = (double *)c->out_f64.p;
     la.S = S;
     la.dbg = nullptr;

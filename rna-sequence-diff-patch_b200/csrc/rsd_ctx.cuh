@@ -59,17 +59,27 @@ struct ModeInfo {
     bool dyadic, i16_ok, i32_ok;
 };
 
+// Plan arrays + hand-off scratch of one batch in flight; the chunks of a host call use one slot each so their
+// kernels may overlap, everything else uses slot 0.
+struct PlanSlot {
+    DevBuf scratch, pair_bin, bins, groups;
+    bool dirty = true;           // bin counters need a memset before the next plan
+    PlanView pv;
+    ModeInfo mi;
+    int64_t n_pairs = 0;
+    void release() { scratch.release(); pair_bin.release(); bins.release(); groups.release(); dirty = true; }
+};
+
 struct rsd_ctx {
     int device = 0;
     bool inited = false;
     pid_t pid = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_sync = nullptr, ev_chunk[RSD_MAX_CHUNKS] = {}, ev_t0[RSD_MAX_CHUNKS] = {}, ev_t1[RSD_MAX_CHUNKS] = {}, ev_done[RSD_MAX_CHUNKS] = {};
-    cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr;
+    cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr, ev_len = nullptr, ev_plans = nullptr;
     double last_ms_override = 0.0;
     bool costs_preloaded = false;
-    bool plan_dirty = true;      // bin counters need a memset before the next plan
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
     int64_t launches = 0;
@@ -80,7 +90,10 @@ struct rsd_ctx {
     F64Costs *d_fc = nullptr;
 
     SeqBufs bufA, bufB, bufX, bufQ;
-    DevBuf out_f64, scratch, plan_pair_bin, plan_bins, plan_groups;
+    DevBuf out_f64;
+    PlanSlot slots[RSD_MAX_CHUNKS];
+    int cur_slot = 0;
+    PlanSlot &ps() { return slots[cur_slot]; }
     DevBuf mat_vals, mat_mask, mat_ab;
     // script / patch
     DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, s_tmp, p_out, p_len, p_err, misc;
@@ -99,6 +112,10 @@ struct rsd_ctx {
                     int64_t n_words, cudaStream_t st);
     int make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_pairs, int C, int allow_twin, double *d_out,
                   cudaStream_t st, PlanView &pv, int64_t max_m, int64_t max_n);
+    int distance_plan(const int32_t *a_len, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n, int bits,
+                      uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
+    int distance_launch(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
+                        const int64_t *b_start, const int32_t *b_len, int64_t max_m, int bits, double *d_out, cudaStream_t st);
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
@@ -110,7 +127,8 @@ struct rsd_ctx {
                         int32_t *n_ops, double *dist, uint8_t *ok, int *mode_out);
     void free_all() {
         bufA.release(); bufB.release(); bufX.release(); bufQ.release(); db.release();
-        DevBuf *all[] = {&out_f64, &scratch, &plan_pair_bin, &plan_bins, &plan_groups, &mat_vals, &mat_mask, &mat_ab,
+        for (PlanSlot &s : slots) s.release();
+        DevBuf *all[] = {&out_f64, &mat_vals, &mat_mask, &mat_ab,
                          &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
                          &db_dist, &db_topi, &db_tops, &db_aux, &db_perm};
         for (DevBuf *b : all) b->release();

@@ -92,12 +92,14 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
         }
     }
     const int baseA = nA * tab.ins, baseB = nB * tab.ins;
+    // gridDim.y > 1 (the short seeding chunk) splits the query batch over blockIdx.y to shorten the pass
+    const int q_lo = (int)((long long)n_queries * blockIdx.y / gridDim.y), q_hi = (int)((long long)n_queries * (blockIdx.y + 1) / gridDim.y);
 
     // One copy of the query loop per number of skipped padding columns (0, 2, .. 16): the column loop is
     // fully unrolled from SKIP on, with no per-row tests.
     auto run_queries = [&](auto skip_tag) {
         constexpr int SKIP = decltype(skip_tag)::value;
-        for (int q = 0; q < n_queries; ++q) {
+        for (int q = q_lo; q < q_hi; ++q) {
             uint32_t H[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) H[c] = 0u;

@@ -1004,7 +1004,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     RSD_OK_OR_RETURN(upload_costs(mi, st));
 
     // chunking: a small first chunk seeds tau cheaply, then large ones; candidate capacity = chunk size
-    const int64_t CH0 = 32768, CH = (int64_t)1 << 20;
+    const int64_t CH0 = 4096, CH = (int64_t)1 << 20;
     const int QB = fast ? 64 : 16;                           // queries per batch
     const int64_t cap = std::min<int64_t>(std::max<int64_t>(db_n, 1), CH);
     const size_t per_q = (size_t)cap * 16 + (size_t)std::max(k, 1) * 16 + 64;
@@ -1037,13 +1037,19 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
             k_build_rowtab<<<(nq * QROWS + 127) / 128, 128, 0, st>>>(q_words, q_start + q0, q_len + q0, nq, bits, QROWS, d_ic, syms_lo, syms_hi, rowtab);
             launches += 1;
         }
+        // a short first chunk (its queries spread over blockIdx.y) seeds tau; the rest goes in equal chunks <= cap
+        const int64_t rest = std::max<int64_t>(db_n - CH0, 0);
+        const int64_t n_main = (rest + cap - 1) / std::max<int64_t>(cap, 1);
+        const int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
         for (int64_t r0 = 0; r0 < db_n;) {
-            const int64_t nr = std::min<int64_t>(r0 == 0 ? std::min(CH0, cap) : cap, db_n - r0);
+            const bool seed = r0 == 0 && db_n > CH0;
+            const int64_t nr = std::min<int64_t>(seed ? CH0 : main_sz, db_n - r0);
             double *alls = all_scores_dev ? all_scores_dev + (size_t)q0 * db_n : nullptr;
             if (fast) {
                 const int64_t threads = (nr + 1) / 2;
                 const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
-                k_search_twin16<<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
+                const dim3 grid((unsigned)((threads + 127) / 128), seed ? (unsigned)std::min(nq, 8) : 1u);
+                k_search_twin16<<<grid, 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
                                                                                       q_len + q0, nq, tab, tk, alls, db_n, 1u);
                 launches += 1;
             } else {

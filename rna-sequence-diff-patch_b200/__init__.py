@@ -15,6 +15,7 @@ Layout:
   ingest.py    FASTA / SeqXML -> packed database (T->U, X->N like the reference's importers)
   eswire.py    edit-script JSON export/import, packed <-> dict scripts, reverse on packed scripts
   dist_search.py  database search sharded over the GPUs of one box (one all_gather)
+  dist_pairs.py   pair batches sharded over the GPUs of one box (balanced by cells, no exchange)
   dropin/      modules importable as `StringEditDistance` / `IRMethods` + cost files
 """
 from ._lib import RsdError, load_library, library_path  # noqa: F401

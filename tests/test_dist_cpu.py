@@ -61,3 +61,63 @@ def test_shard_bounds_cover_and_balance():
         sums = [int(lens[lo:hi].sum()) for lo, hi in b]
         assert max(sums) - min(sums) <= 64
     assert shard_bounds(np.zeros(0, np.int64), 4) == [(0, 0)] * 4
+
+
+class _OracleEngine:
+    """Stands in for Engine in the CPU-only world_size-2 test of the pair-list sharding (no GPU here)."""
+
+    def __init__(self, costs):
+        self.costs = costs
+
+    def distance_batch(self, A, B, force_mode=0):
+        from oracle import oracle as O
+        import rna_sequence_diff_patch_b200 as R
+        from rna_sequence_diff_patch_b200.encoding import unpack
+        ca, oa = unpack(A); cb, ob = unpack(B)
+        return O.distance_batch(ca, oa, cb, ob, self.costs)
+
+
+def _pairs_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import json
+    import torch.distributed as dist
+    from oracle import oracle as O
+    import rna_sequence_diff_patch_b200 as R
+    from rna_sequence_diff_patch_b200.dist_pairs import ShardedPairs
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "user_costs.json")))
+    rng = np.random.default_rng(11)
+    n = 501
+    la = rng.integers(0, 60, size=n); lb = rng.integers(0, 60, size=n)
+    oa = np.zeros(n + 1, np.int64); np.cumsum(la, out=oa[1:]); ob = np.zeros(n + 1, np.int64); np.cumsum(lb, out=ob[1:])
+    ca = rng.integers(0, 4, size=int(oa[-1]), dtype=np.uint8); cb = rng.integers(0, 4, size=int(ob[-1]), dtype=np.uint8)
+    A = R.pack((ca, oa)); B = R.pack((cb, ob))
+    got = ShardedPairs(_OracleEngine(costs), rank, world).distance_batch(A, B)
+    want = O.distance_batch(ca, oa, cb, ob, costs)
+    np.save(os.path.join(tmp, f"ok{rank}.npy"), np.array([np.array_equal(got, want)]))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_pairs(tmp_path):
+    import torch.multiprocessing as mp
+    import __graft_entry__ as G
+    G.build()
+    port = 30100 + (os.getpid() % 500)
+    mp.spawn(_pairs_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(np.load(os.path.join(str(tmp_path), f"ok{r}.npy"))[0] for r in range(2))
+
+
+def test_pair_shard_bounds_balance_cells():
+    sys.path.insert(0, ROOT)
+    from rna_sequence_diff_patch_b200.dist_pairs import pair_shard_bounds
+    rng = np.random.default_rng(2)
+    la = rng.integers(100, 301, size=20011); lb = rng.integers(100, 301, size=20011)
+    la[:5000] = 300; lb[:5000] = 300                                 # heavy head: equal counts would be unbalanced
+    cells = la.astype(np.int64) * lb
+    for world in (1, 2, 3, 8):
+        b = pair_shard_bounds(la, lb, world)
+        assert b[0][0] == 0 and b[-1][1] == 20011 and all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        sums = [int(cells[lo:hi].sum()) for lo, hi in b]
+        assert max(sums) - min(sums) <= 2 * 300 * 300
+    assert pair_shard_bounds(np.zeros(0, np.int32), np.zeros(0, np.int32), 3) == [(0, 0)] * 3

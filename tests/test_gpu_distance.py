@@ -247,3 +247,21 @@ def test_shared_sequence_layout_falls_back_to_whole_copy(R, eng, golden):
     sub = rng.choice(n, size=300, replace=False)
     want = oracle_batch([q] * 300, [b[k] for k in sub], golden["default_costs"])
     assert np.array_equal(out[sub], want)
+
+
+def test_pair_list_shards_concatenate_to_the_unsharded_result(R, eng, golden):
+    """8e: contiguous pair ranges balanced by cells, scored independently (3 emulated ranks on one GPU)."""
+    from rna_sequence_diff_patch_b200.dist_pairs import ShardedPairs
+    rng = np.random.default_rng(17)
+    a = rand_seqs(rng, 4000, 0, 90, "AGCUN"); b = rand_seqs(rng, 4000, 0, 90, "AGCUN")
+    A = R.pack(a); B = R.pack(b)
+    eng.set_costs(golden["default_costs"])
+    whole = eng.distance_batch(A, B)
+    parts = []
+    for rank in range(3):
+        sp = ShardedPairs(eng, rank, 3)
+        bounds, (lo, hi) = sp.local_range(A, B)
+        parts.append(sp.distance_batch(A, B))                 # no process group: returns the local range
+        assert parts[-1].shape[0] == hi - lo
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert np.array_equal(whole, oracle_batch(a, b, golden["default_costs"]))

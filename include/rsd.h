@@ -174,6 +174,21 @@ int rsd_db_search_topk_dev(rsd_ctx *ctx, const uint32_t *q_words_dev, const int6
                            const int32_t *q_len_dev, int64_t n_queries, int64_t max_qlen, int bits,
                            uint32_t q_symmask, int k, int force_mode,
                            int64_t *top_idx_dev, double *top_score_dev, int *mode_out, void *stream);
+/* Set / multiset / TF-vector similarity of one query against the loaded database — the other scorers
+ * of search_collection (IRMethods.py:443-477 with the measures of IRMethods.py:49-389; documents'
+ * 'tf' vectors are rebuilt on the device from the sequences, what fa_import.py:49 stores).  `method`
+ * is one of RSD_SIM_*; q_codes are symbol codes 0..14.  all_scores (may be NULL) receives db_n fp64
+ * scores in record order; k > 0 also returns the top-k with the key (score desc, global index asc).
+ * Scores equal the reference's numpy arithmetic bit for bit; its 0/0 cases come back as NaN and are
+ * never ranked.  The cost tables play no role here. */
+enum {
+    RSD_SIM_SET_INTERSECTION = 0, RSD_SIM_SET_JACCARD = 1, RSD_SIM_SET_DICE = 2,
+    RSD_SIM_MULTI_INTERSECTION = 3, RSD_SIM_MULTI_JACCARD = 4, RSD_SIM_MULTI_DICE = 5,
+    RSD_SIM_COSINE = 6, RSD_SIM_PEARSON = 7, RSD_SIM_EUCLIDEAN = 8, RSD_SIM_MANHATTAN = 9,
+    RSD_SIM_TANIMOTO = 10, RSD_SIM_DICE = 11
+};
+int rsd_db_similarity(rsd_ctx *ctx, const uint8_t *q_codes, int32_t q_len, int method, int k,
+                      int64_t *top_idx, double *top_score, double *all_scores);
 /* merge G shards' top-k lists (each n_queries*k, shard-major) with the same key — the reduction
  * run after the gather (host side, O(G*k) per query) */
 int rsd_topk_merge(const int64_t *idx, const double *score, int n_shards, int64_t n_queries, int k,

@@ -59,6 +59,7 @@ SIGNATURES = {
     "rsd_db_free": (ci, [vp]),
     "rsd_db_search_topk": (ci, [vp, u32p, i64p, i32p, i64, i64, ci, u32, ci, ci, i64p, f64p, f64p, intp]),
     "rsd_db_search_topk_dev": (ci, [vp, vp, vp, vp, i64, i64, ci, u32, ci, ci, vp, vp, intp, vp]),
+    "rsd_db_similarity": (ci, [vp, u8p, C.c_int32, ci, ci, i64p, f64p, f64p]),
     "rsd_topk_merge": (ci, [i64p, f64p, ci, i64, ci, i64p, f64p]),
     "rsd_long_pair": (ci, [vp, u8p, i64, u8p, i64, ci, ci, i64, u8p, i32p, i32p, i64p, f64p, intp]),
     "rsd_launch_count": (i64, [vp]),

@@ -176,7 +176,7 @@ __global__ void k_score_filter(const double *__restrict__ dist, int64_t rec0, in
 __global__ void k_topk_init(TopkState tk, int n_queries) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_queries) return;
-    tk.tau_s[q] = -1.0; tk.tau_i[q] = 0x7fffffffffffffffLL;      // accept everything (scores are > 0)
+    tk.tau_s[q] = -INFINITY; tk.tau_i[q] = 0x7fffffffffffffffLL;  // accept everything
     tk.cand_n[q] = 0;
     for (int r = 0; r < tk.k; ++r) { tk.best_s[(size_t)q * tk.k + r] = 0.0; tk.best_i[(size_t)q * tk.k + r] = -1; }
 }

@@ -17,6 +17,7 @@
 #include "k_ubench.cuh"
 #include "k_script.cuh"
 #include "k_search.cuh"
+#include "k_sim.cuh"
 #include "k_long.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -964,7 +965,7 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
 
 extern "C" int rsd_db_free(rsd_ctx *c) {
     if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
-    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_perm.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); }
+    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_perm.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); c->sim_scores.release(); c->sim_aux.release(); }
     c->db_loaded = false; c->db_n = 0;
     return RSD_OK;
 }
@@ -1115,6 +1116,75 @@ extern "C" int rsd_db_search_topk(rsd_ctx *c, const uint32_t *q_words, const int
         RSD_CUDA(cudaMemcpyAsync(top_score, c->s_oj.p, sizeof(double) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
     }
     if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores, c->out_f64.p, sizeof(double) * (size_t)n_queries * c->db_n, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaStreamSynchronize(st));
+    return RSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// set / multiset / TF-vector similarity search
+// ------------------------------------------------------------------------------------------------
+extern "C" int rsd_db_similarity(rsd_ctx *c, const uint8_t *q_codes, int32_t q_len, int method, int k,
+                                 int64_t *top_idx, double *top_score, double *all_scores) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (method < 0 || method >= RSD_SIM_COUNT) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: unknown method %d", method);
+    if (q_len < 0 || (q_len > 0 && !q_codes)) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: bad query");
+    if (k < 0 || k > RSD_TOPK_MAX) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: k must be in 0..%d", RSD_TOPK_MAX);
+    if (k > 0 && (!top_idx || !top_score)) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: NULL top-k output");
+    for (int32_t i = 0; i < q_len; ++i)
+        if (q_codes[i] >= 15) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: query code %u at %d is not a symbol", q_codes[i], i);
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (!c->db_loaded) return rsd_fail(RSD_EINVAL, "rsd_db_similarity: no database loaded (rsd_db_load)");
+    cudaStream_t st = c->stream;
+    c->timed = false; c->last_ms_override = 0.0;
+    const int64_t n = c->db_n;
+    RSD_OK_OR_RETURN(c->sim_codes.ensure((size_t)q_len + 16));
+    RSD_OK_OR_RETURN(c->sim_q.ensure(sizeof(SimQuery)));
+    RSD_OK_OR_RETURN(c->sim_scores.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    if (q_len) RSD_CUDA(cudaMemcpyAsync(c->sim_codes.p, q_codes, (size_t)q_len, cudaMemcpyHostToDevice, st));
+    if (c->timing) RSD_CUDA(cudaEventRecord(c->ev0, st));
+    k_sim_query<<<1, 32, 0, st>>>((const uint8_t *)c->sim_codes.p, q_len, (SimQuery *)c->sim_q.p);
+    c->launches += 1;
+    const uint32_t *dbw = (const uint32_t *)c->db.words.p; const int64_t *dbs = (const int64_t *)c->db.start.p; const int32_t *dbl = (const int32_t *)c->db.len.p;
+    double *scores = (double *)c->sim_scores.p;
+    if (n > 0) {
+        if (method < RSD_SIM_COSINE) {
+            k_sim_small<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dbw, dbs, dbl, n, c->db_bits, (const int64_t *)c->db_perm.p, c->db_base,
+                                                                     (const SimQuery *)c->sim_q.p, method, scores);
+        } else {
+            const unsigned grid = (unsigned)std::min<int64_t>((n + 3) / 4, (int64_t)c->sm_count * 16);
+            k_sim_tf<<<grid, 128, 0, st>>>(dbw, dbs, dbl, n, c->db_bits, (const int64_t *)c->db_perm.p, c->db_base,
+                                           (const SimQuery *)c->sim_q.p, method, scores);
+        }
+        c->launches += 1;
+    }
+    if (k > 0) {
+        const int64_t CH0 = 4096, cap = std::min<int64_t>(std::max<int64_t>(n, 1), (int64_t)1 << 20);
+        RSD_OK_OR_RETURN(c->sim_aux.ensure((size_t)cap * 16 + (size_t)k * 16 + 256));
+        unsigned char *aux = (unsigned char *)c->sim_aux.p;
+        TopkState tk{};
+        tk.k = k; tk.cap = cap;
+        tk.cand_s = (double *)aux; aux += (size_t)cap * 8;
+        tk.cand_i = (int64_t *)aux; aux += (size_t)cap * 8;
+        tk.best_s = (double *)aux; aux += (size_t)k * 8;
+        tk.best_i = (int64_t *)aux; aux += (size_t)k * 8;
+        tk.tau_s = (double *)aux; aux += 8;
+        tk.tau_i = (int64_t *)aux; aux += 8;
+        tk.cand_n = (int *)aux;
+        k_topk_init<<<1, 64, 0, st>>>(tk, 1);
+        c->launches += 1;
+        for (int64_t r0 = 0; r0 < n;) {
+            const int64_t nr = std::min<int64_t>(r0 == 0 ? std::min(CH0, cap) : cap, n - r0);
+            k_sim_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(scores, r0, nr, c->db_base, tk);
+            k_topk_fold<<<1, 256, 0, st>>>(tk);
+            c->launches += 2;
+            r0 += nr;
+        }
+        RSD_CUDA(cudaMemcpyAsync(top_idx, tk.best_i, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, st));
+        RSD_CUDA(cudaMemcpyAsync(top_score, tk.best_s, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, st));
+    }
+    if (c->timing) { RSD_CUDA(cudaEventRecord(c->ev1, st)); c->timed = true; }
+    if (all_scores && n > 0) RSD_CUDA(cudaMemcpyAsync(all_scores, scores, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    RSD_CUDA(cudaGetLastError());
     RSD_CUDA(cudaStreamSynchronize(st));
     return RSD_OK;
 }

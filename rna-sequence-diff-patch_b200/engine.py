@@ -185,6 +185,23 @@ class Engine:
         self.last_mode = mode.value
         return mode.value
 
+    # ---- other scorers of search_collection (set / multiset / TF-vector measures) ---------------------------
+    SIM_METHODS = ("set_intersection_similarity", "set_jaccard_similarity", "set_dice_similarity",
+                   "multi_intersection_similarity", "multi_jaccard_similarity", "multi_dice_similarity",
+                   "cosine", "pearson", "euclidian_distance", "manhattan_distance", "tanimoto_distance", "dice_dist")
+
+    def db_similarity(self, query_codes: np.ndarray, method, k: int = 0, want_scores: bool = True):
+        """IR:443-477 for the measures of IR:49-389 against the loaded database.
+        -> (all_scores f64[n_db] | None, top_idx int64[k], top_score f64[k])."""
+        mid = self.SIM_METHODS.index(method) if isinstance(method, str) else int(method)
+        q = np.ascontiguousarray(query_codes, np.uint8)
+        qq = q if q.shape[0] else np.zeros(1, np.uint8)
+        alls = np.zeros(self._db_n, np.float64) if want_scores else None
+        idx = np.full(max(k, 1), -1, np.int64); sc = np.zeros(max(k, 1), np.float64)
+        check(self._lib.rsd_db_similarity(self._ctx, ptr(qq, _u8), int(q.shape[0]), mid, int(k), ptr(idx, _i64), ptr(sc, _f64),
+                                          ptr(alls, _f64) if want_scores and self._db_n else None))
+        return alls, idx[:k], sc[:k]
+
     def topk_merge(self, idx: np.ndarray, score: np.ndarray):
         return topk_merge(idx, score)
 

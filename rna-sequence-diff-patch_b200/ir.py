@@ -1,8 +1,10 @@
-"""ir.py — the Wagner–Fischer part of the reference's IRMethods.py on top of the CUDA engine.
+"""ir.py — the search side of the reference's IRMethods.py on top of the CUDA engine.
 
 Mirrors: wf_score IR:435-440, the wf_score branch of search_collection IR:443-447,466-477 (one
 batched GPU scan of the collection instead of one wagnerFisher call per document), and the
-stable descending top-k of performance.py:12-15 / gui.py:573,593."""
+stable descending top-k of performance.py:12-15 / gui.py:573,593; and the other scorers of
+search_collection — set / multiset / TF-vector measures, IR:49-389 — as one GPU pass over the collection
+(similarity_collection)."""
 from __future__ import annotations
 
 from operator import itemgetter
@@ -36,6 +38,32 @@ def score_collection(query: str, sequences, costs: dict, engine=None):
     finally:
         eng.db_free()
     return [(s, float(v)) for s, v in zip(sequences, scores[0])]
+
+
+SIM_METHODS = ("set_intersection_similarity", "set_jaccard_similarity", "set_dice_similarity",
+               "multi_intersection_similarity", "multi_jaccard_similarity", "multi_dice_similarity",
+               "cosine", "pearson", "euclidian_distance", "manhattan_distance", "tanimoto_distance", "dice_dist")
+
+
+def similarity_collection(query: str, sequences, method: str, engine=None):
+    """[(sequence, method(query, sequence))] in collection order for one of SIM_METHODS — what
+    search_collection(query, 'tf', collection, <method>) returns (IR:449-477), one GPU pass.  The documents'
+    stored 'tf' vectors are rebuilt from the sequences on the device (they are convert_to_tf_vector(sequence),
+    fa_import.py:49).  Unknown symbols raise KeyError (the reference: KeyError IR:106 / ValueError IR:155)."""
+    if method not in SIM_METHODS:
+        raise ValueError(f"unknown similarity method {method!r}")
+    sequences = list(sequences)
+    if not sequences:
+        return []
+    from .encoding import encode
+    eng = engine or get_engine()
+    qc = encode(query)
+    eng.db_load(pack(sequences, bits=4))
+    try:
+        scores, _, _ = eng.db_similarity(qc, method)
+    finally:
+        eng.db_free()
+    return [(s, float(v)) for s, v in zip(sequences, scores)]
 
 
 def top_k(scores, k):

@@ -127,9 +127,20 @@ def c5(eng, n_rec, nq=64, k=10, reps=3):
         idx, sc = eng.db_search_topk(Q, k)
         if r:
             ts.append(time.perf_counter() - t0); kms.append(eng.last_kernel_ms())
+    # the other scorers of search_collection on the same database (8f rank 4): one query, all scores + top-k on device
+    sim = {}
+    db_bytes = float(db.words.nbytes + n_rec * (8 + 4 + 8 + 8))           # words + start + len + perm read, score written
+    for method in ("set_jaccard_similarity", "multi_dice_similarity", "cosine", "pearson"):
+        ms = []
+        for r in range(3):
+            eng.db_similarity(qs[0], method, k=k, want_scores=False)
+            if r:
+                ms.append(eng.last_kernel_ms())
+        m = float(np.mean(ms))
+        sim[method] = {"ms_per_query": m, "records_per_s": n_rec / (m * 1e-3), "hbm_gbs_algorithmic": db_bytes / (m * 1e-3) * 1e-9}
     eng.db_free()
     t, kk = float(np.mean(ts)), float(np.mean(kms)) * 1e-3
-    return {"config": "C5", "records": n_rec, "queries": nq, "k": k, "cells": cells, "mode": eng.last_mode,
+    return {"config": "C5", "similarity_search": sim, "records": n_rec, "queries": nq, "k": k, "cells": cells, "mode": eng.last_mode,
             "e2e_gcups": cells / t * 1e-9, "e2e_s": t, "device_gcups": cells / kk * 1e-9, "device_s": kk,
             "top1_scores_head": sc[:3, 0].tolist()}
 

@@ -85,7 +85,7 @@ def main():
         alpha = [SYM[:4], SYM[:4], SYM[:4] + "N", SYM, SYM[:2], "ACGUYR"][int(rng.integers(0, 6))]
         ckind = ["default", "user", "dyadic", "int", "decimal"][int(rng.integers(0, 5))]
         lkind = ["tiny", "short", "c2", "kb", "skew", "wide"][int(rng.integers(0, 6))]
-        what = ["dist", "dist", "script", "search"][int(rng.integers(0, 4))]
+        what = ["dist", "dist", "script", "search", "long"][int(rng.integers(0, 5))]
         costs = random_costs(rng, ckind)
         eng.set_costs(costs)
         force = int(rng.choice([0, 0, 0, 2, 3]))
@@ -122,6 +122,24 @@ def main():
                         and np.array_equal(res["oj"][p, :k], oj[p, :k])
                 cells += float((np.diff(oa).astype(np.float64) * np.diff(ob)).sum())
                 desc = f"script n={n} mode={eng.last_mode}"
+            elif what == "long":
+                m, n2 = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+                al = np.array([SYM.index(ch) for ch in alpha], np.uint8)
+                a1 = al[rng.integers(0, len(al), size=m)]
+                if rng.random() < 0.5:                           # homologous: the interesting tie structure
+                    keep = rng.random(m) > 0.03
+                    b1 = a1[keep].copy()
+                    hit = rng.random(b1.shape[0]) < 0.05
+                    b1[hit] = al[rng.integers(0, len(al), size=int(hit.sum()))]
+                    if b1.shape[0] == 0:
+                        b1 = a1[:1].copy()
+                else:
+                    b1 = al[rng.integers(0, len(al), size=n2)]
+                res = eng.long_pair(a1, b1, force_mode=force if force != 2 else 0)
+                ops, oi, oj, d = O.canonical_script(O.decode(a1), O.decode(b1), costs)
+                ok = res["dist"] == d and np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
+                cells += float(m) * b1.shape[0]
+                desc = f"long {m}x{b1.shape[0]} mode={eng.last_mode}"
             else:
                 n = int(rng.choice([1, 50, 3000, 40000]))
                 lens = rng.integers(0 if rng.random() < 0.3 else 20, int(rng.choice([32, 33, 60])), size=n)

@@ -112,6 +112,25 @@ def _claim_stdout():
     return real
 
 
+def bind_near_gpu(index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs next to its GPU, as NVML reports
+    them — with 8 ranks the host->device copies otherwise cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] no CPU affinity for GPU {index}: {e}")
+        return None
+
+
 def main():
     out = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -171,6 +190,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else None      # pinned buffers are first-touched after this
+    if numa:
+        config["host"] = f"each rank runs on the {numa} CPUs NVML lists next to its GPU (pinned buffers first-touched there)"
 
     ca, oa, cb, ob = gen_pairs(args.pairs, SEEDS[args.workload] + rank, alpha)
     cells = float(((oa[1:] - oa[:-1]) * (ob[1:] - ob[:-1])).sum())

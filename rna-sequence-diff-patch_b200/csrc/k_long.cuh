@@ -216,10 +216,160 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
     }
 }
 
+// Integer keys in 32 bits, compared modulo 2^32.  The (cost << S | steps) key of a 50 kb pair needs ~36
+// bits, but a cell only ever compares candidates that lie a bounded distance apart (neighbouring cells
+// differ by at most (ins + del + max|w|) << S), so the sign of the 32-bit wrapped difference is the sign of
+// the true difference and min(a, b) = a + min(b - a, 0) is exact.  The host checks that bound.  The fp64
+// pipe's long latency sat on the per-row dependency chain of the double-carried keys; here the chain per
+// cell is VIADDMNMX + IADD.  Direction bits are the sign bits of the two differences, as in k_script_fwd.
+// The full 64-bit key of cell (m, n) — needed for the distance — is rebuilt from bounded row-to-row
+// differences of each lane's last column.  Boundary words between panels are (1 << 32 | key): the high
+// half doubles as the "published" tag against the 0x80.. sentinel.
+template <int C>
+__global__ void __launch_bounds__(32)
+k_long_fwd32(LongArgs la, const IntCosts *__restrict__ icp) {
+    __shared__ uint32_t s_w[256];
+    __shared__ uint32_t s_pub[16];
+    __shared__ uint8_t s_a[64];
+    for (int k = threadIdx.x; k < 256; k += 32)
+        s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << la.S) - 1);        // (w << S) - 1, fits (host check)
+    __syncwarp();
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x;                       // panel
+    const int m = la.m, n = la.n;
+    const int col0 = (w * 32 + lane) * C;
+    const bool strip_on = col0 < n;
+    int bc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) bc[c] = (col0 + c < n) ? la.b[col0 + c] : 0;
+    uint32_t H[C], acc[C], bca[C];                  // bca: shared-memory byte address of the column's table entry in row 0
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+    for (int c = 0; c < C; ++c) { H[c] = 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc[c]; }
+    uint32_t last = 0u, prev_recv = 0u;
+    long long full = 0;                             // exact key of this lane's last column, current row
+    const unsigned long long *bin = w > 0 ? (const unsigned long long *)la.bound + (size_t)(w - 1) * m : nullptr;
+    unsigned long long *bout = (unsigned long long *)la.bound + (size_t)w * m;
+    const bool publish = (w + 1 < la.n_panels);
+    uint32_t *dcol = la.dirs + col0;
+    const int steps = m + 31 + 16;                  // + one block so the last rows get published
+    unsigned long long dbg_t0 = 0, dbg_poll = 0, dbg_pub = 0, dbg_ld = 0, dbg_loop = 0;
+    if (la.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    uint8_t pf0 = ((unsigned)(lane - 31) < (unsigned)m) ? la.a[lane - 31] : (uint8_t)0;      // rows of block 0
+    uint8_t pf1 = (lane < 15 && 1 + lane < m) ? la.a[1 + lane] : (uint8_t)0;
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += 16) {
+        long long c0 = la.dbg ? clock64() : 0;
+        const uint32_t last_at_block_start = last;
+        if (publish && lane < 16) {
+            const int r = t0 - 47 + lane;
+            if (r >= 0 && r < m) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
+        }
+        __syncwarp();
+        if (la.dbg) { long long c1 = clock64(); dbg_pub += (unsigned long long)(c1 - c0); c0 = c1; }
+        uint32_t bval = 0u;
+        if (w > 0) {
+            const bool mine = lane < 16 && t0 + lane < m;
+            unsigned long long raw = 0ull;
+            do {
+                if (mine) raw = ld_poll_u64(bin + t0 + lane);
+            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));      // warp-uniform exit (see k_long_fwd)
+            bval = (uint32_t)raw;
+        }
+        if (la.dbg) { __syncwarp(); long long c1 = clock64(); dbg_poll += (unsigned long long)(c1 - c0); c0 = c1; }
+        unsigned long long codes = 0ull;
+        {
+            // this block's source symbols were fetched one block ahead; fetch the next block's now so the
+            // global-load latency hides behind the 16 rows below
+            s_a[lane] = pf0;
+            if (lane < 15) s_a[32 + lane] = pf1;
+            const int r0 = t0 + 16 - 31 + lane, r1 = t0 + 16 + 1 + lane;
+            pf0 = ((unsigned)r0 < (unsigned)m) ? la.a[r0] : (uint8_t)0;
+            if (lane < 15) pf1 = ((unsigned)r1 < (unsigned)m) ? la.a[r1] : (uint8_t)0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) codes |= (unsigned long long)s_a[31 - lane + k] << (4 * k);
+            __syncwarp();
+        }
+        if (la.dbg) { __syncwarp(); long long c1 = clock64(); dbg_ld += (unsigned long long)(c1 - c0 + (codes & 0)); c0 = c1; }
+        // Blocks in which every lane is inside its rows (all but the first and last few) run a copy of the
+        // row loop without the per-row activity test: no branch for the scheduler to work around.
+        auto run16 = [&](auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const int t = t0 + k;
+            const int i = t - lane;
+            const bool row_on = STEADY || (strip_on && (unsigned)i < (unsigned)m);
+            // phase A — everything that does not involve the left neighbour (the table row, diag + w, the
+            // DEL/UPD decision) is issued first and runs while the shuffle below is in flight
+            const uint32_t rowoff = ((uint32_t)(codes >> (4 * k)) & 15u) << 6;        // byte offset of the table row
+            uint32_t t2[C], wv[C]; int e1[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv[c]) : "r"(bca[c] + rowoff));
+            {
+                uint32_t diag = prev_recv;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t up = H[c];
+                    const uint32_t x = diag + wv[c];
+                    e1[c] = (int)(x - up);                                         // < 0  <=>  diagonal strictly better than up (ties keep DEL)
+                    t2[c] = up + (uint32_t)min(e1[c], 0);                          // min(up, x) modulo 2^32
+                    diag = up;
+                }
+            }
+            uint32_t recv = __shfl_up_sync(RSD_FULL, last, 1);
+            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, k);
+            if (lane == 0) recv = w > 0 ? b0 : 0u;
+            if (row_on) {
+                // phase B — the dependency chain of the row: per cell VIADDMNMX + IADD
+                uint32_t left = recv;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int e2 = (int)(t2[c] - left);                            // < 0  <=>  left loses (ties keep INS)
+                    const uint32_t hn = t2[c] + (uint32_t)__viaddmin_s32((int)left, -(int)t2[c], 0);   // min(left, t2)
+                    H[c] = hn; left = hn;
+                    acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);             // "not INS"
+                    acc[c] = __funnelshift_l((uint32_t)e1[c], acc[c], 1);          // then "UPD rather than DEL"
+                }
+                last = left; prev_recv = recv;
+                if ((i & 15) == 15 || i == m - 1) {
+                    const int sh = 2 * (15 - (i & 15));
+                    uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
+#pragma unroll
+                    for (int c = 0; c < C; c += 4)
+                        dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
+                }
+            }
+            if (lane == 31) s_pub[k] = last;
+        }
+        };
+        if (t0 >= 31 && t0 + 15 <= m - 1) run16(std::true_type{}); else run16(std::false_type{});
+        full += (long long)(int)(last - last_at_block_start);          // <= 16 bounded row-to-row differences (host check)
+        __syncwarp();
+        if (la.dbg) dbg_loop += (unsigned long long)(clock64() - c0);
+    }
+    if (la.dbg && lane == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        la.dbg[w * 8 + 0] = dbg_t0; la.dbg[w * 8 + 1] = t1; la.dbg[w * 8 + 2] = dbg_poll; la.dbg[w * 8 + 3] = dbg_pub; la.dbg[w * 8 + 4] = dbg_ld; la.dbg[w * 8 + 5] = dbg_loop;
+    }
+    if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
+        const int cl = (n - 1) - col0;
+        uint32_t res = 0u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
+        // `full` is the exact key of column C-1 at row m; column cl lies at most C-1 cells to its left
+        const long long hkey = full + (long long)(int)(res - H[C - 1]);
+        const long long key = hkey + (long long)m * (((long long)icp->del << la.S) + 1) + (long long)n * (((long long)icp->ins << la.S) + 1);
+        la.dist[0] = (double)(key >> la.S) / (double)(1 << icp->scale_log2);
+    }
+}
+
 // Traceback of the long pair: one warp.  The walk is a chain of ~m+n dependent reads, so the warp
 // stages a 64-row x 64-column tile of direction words around the current cell in shared memory with
-// coalesced loads, lane 0 walks inside the tile (shared-memory latency per step instead of an HBM
-// miss), and the warp reloads when the path leaves the tile.  Ops are written sink->origin from the
+// coalesced loads, the warp walks inside the tile (whole diagonal runs per iteration, shared-memory
+// latency instead of an HBM miss per step), and reloads when the path leaves the tile.  Ops are written sink->origin from the
 // end of tmp[0 .. m+n).
 __global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint32_t *__restrict__ dirs, int n_pad,
                                                        uint8_t *__restrict__ tmp, int32_t *__restrict__ n_ops) {
@@ -235,16 +385,24 @@ __global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint3
         for (int r = 0; r < nr; ++r)
             for (int c = lane; c < nc; c += 32) tile[r][c] = dirs[(size_t)(rb_lo + r) * n_pad + c_lo + c];
         __syncwarp();
-        if (lane == 0) {
-            const int i_min = rb_lo * 16;
-            while (i > i_min && j > c_lo) {
-                const uint32_t wv = tile[((i - 1) >> 4) - rb_lo][(j - 1) - c_lo];
-                const uint32_t code = dir_decode(wv, i - 1);
-                tmp[--pos] = (uint8_t)code;
-                if (code == 0u) --j; else if (code == 1u) --i; else { --i; --j; }
+        // Inside the tile the warp walks together: lane l looks at the cell l steps up the diagonal from
+        // (i, j); the leading run of UPD cells (the common move between similar sequences) is emitted in
+        // one go, then the single INS / DEL that ended it.  i, j, pos stay warp-uniform.
+        const int i_min = rb_lo * 16;
+        while (i > i_min && j > c_lo) {
+            const int ii = i - lane, jj = j - lane;
+            uint32_t code = 3u;                                            // outside the tile
+            if (ii > i_min && jj > c_lo) code = dir_decode(tile[((ii - 1) >> 4) - rb_lo][(jj - 1) - c_lo], ii - 1);
+            const unsigned diag_mask = __ballot_sync(RSD_FULL, code == 2u);
+            const int run = diag_mask == 0xffffffffu ? 32 : __ffs(~diag_mask) - 1;
+            if (lane < run) tmp[pos - 1 - lane] = (uint8_t)2;
+            pos -= run; i -= run; j -= run;
+            if (run < 32) {
+                const uint32_t nxt = __shfl_sync(RSD_FULL, code, run);
+                if (nxt == 0u) { if (lane == 0) tmp[pos - 1] = (uint8_t)0; --pos; --j; }
+                else if (nxt == 1u) { if (lane == 0) tmp[pos - 1] = (uint8_t)1; --pos; --i; }
             }
         }
-        i = __shfl_sync(RSD_FULL, i, 0); j = __shfl_sync(RSD_FULL, j, 0); pos = __shfl_sync(RSD_FULL, pos, 0);
         __syncwarp();
     }
     if (lane == 0) {

@@ -1233,7 +1233,16 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     const int n_panels = (int)((n + 32 * C - 1) / (32 * C));
     const int64_t n_pad = (int64_t)n_panels * 32 * C;
     int per_sm = 0;
-    const void *kfn = f64 ? (C == 4 ? (const void *)k_long_fwd<true, 4> : C == 16 ? (const void *)k_long_fwd<true, 16> : (const void *)k_long_fwd<true, 8>)
+    // 32-bit modular keys when every pair of compared candidates stays within 2^30 of each other
+    bool key32 = false;
+    if (!f64 && !getenv("RSD_LONG_WIDE")) {
+        long long maxc = std::max<long long>(mi.ic.ins, mi.ic.del);
+        for (int x = 0; x < 16; ++x) for (int y = 0; y < 16; ++y)
+            if ((symmask >> x & 1) && (symmask >> y & 1)) maxc = std::max<long long>(maxc, std::llabs((long long)mi.ic.w[x][y]));
+        key32 = S <= 24 && ((32 * maxc + 64) << S) < (1ll << 30);     // covers 16 rows of drift (the per-block key tracking)
+    }
+    const void *kfn = key32 ? (C == 4 ? (const void *)k_long_fwd32<4> : C == 16 ? (const void *)k_long_fwd32<16> : (const void *)k_long_fwd32<8>) :
+                      f64 ? (C == 4 ? (const void *)k_long_fwd<true, 4> : C == 16 ? (const void *)k_long_fwd<true, 16> : (const void *)k_long_fwd<true, 8>)
                           : (C == 4 ? (const void *)k_long_fwd<false, 4> : C == 16 ? (const void *)k_long_fwd<false, 16> : (const void *)k_long_fwd<false, 8>);
     RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32, 0));
     if ((int64_t)per_sm * c->sm_count < n_panels)
@@ -1261,8 +1270,9 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     RSD_CUDA(cudaMemsetAsync(la.bound, 0x80, (size_t)n_panels * (size_t)m * 8, st));      // sentinel = "not published yet"
     const IntCosts *dic = c->d_ic; const F64Costs *dfc = c->d_fc;
     void *args[] = {&la, &dic, &dfc};
+    void *args32[] = {&la, &dic};
     if (c->timing) RSD_CUDA(cudaEventRecord(c->ev0, st));
-    RSD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(n_panels), dim3(32), args, 0, st));
+    RSD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(n_panels), dim3(32), key32 ? args32 : args, 0, st));
     c->launches += 1;
     if (want_script) {
         RSD_OK_OR_RETURN(c->s_tmp.ensure((size_t)(m + n) + 64));

@@ -382,8 +382,17 @@ __global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint3
         const int rb_hi = (i - 1) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
         const int c_hi = j - 1, c_lo = max(c_hi - TC + 1, 0);
         const int nr = rb_hi - rb_lo + 1, nc = c_hi - c_lo + 1;
-        for (int r = 0; r < nr; ++r)
-            for (int c = lane; c < nc; c += 32) tile[r][c] = dirs[(size_t)(rb_lo + r) * n_pad + c_lo + c];
+        {
+            // all loads of the tile are issued before the first store: one memory latency per tile, not one per word
+            uint32_t v[TR * (TC / 32)];
+#pragma unroll
+            for (int q = 0; q < TR * (TC / 32); ++q) {
+                const int r = q / (TC / 32), c = lane + 32 * (q % (TC / 32));
+                v[q] = (r < nr && c < nc) ? __ldg(dirs + (size_t)(rb_lo + r) * n_pad + c_lo + c) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < TR * (TC / 32); ++q) tile[q / (TC / 32)][lane + 32 * (q % (TC / 32))] = v[q];
+        }
         __syncwarp();
         // Inside the tile the warp walks together: lane l looks at the cell l steps up the diagonal from
         // (i, j); the leading run of UPD cells (the common move between similar sequences) is emitted in

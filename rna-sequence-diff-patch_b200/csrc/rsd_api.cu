@@ -1227,7 +1227,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     RSD_OK_OR_RETURN(c->upload_costs(mi, st));
     // 4 columns per lane: the forward pass is latency-bound (one warp per panel, a dependent chain per
     // row), so narrow panels = more panels in flight win until the panel pipeline lag dominates
-    // (measured at 50 kb: C=4 15.4 ms, C=8 22.8 ms, C=16 19.9 ms).
+    // (measured at 50 kb, 32-bit keys: C=4 10.8 ms, C=8 10.9 ms, C=16 13.6 ms; double-carried keys: 15.4 / 22.8 / 19.9 ms).
     int C = 4;
     if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) C = v; }
     const int n_panels = (int)((n + 32 * C - 1) / (32 * C));

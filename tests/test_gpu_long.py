@@ -98,3 +98,29 @@ def test_c4_shape_properties(R, eng, golden):
     off_a = np.array([0, a.shape[0]], np.int64); off_b = np.array([0, b.shape[0]], np.int64)
     d = eng.distance_batch(R.pack((a, off_a)), R.pack((b, off_b)))
     assert d[0] == res["dist"]
+
+
+def test_wide_key_fallback_paths_agree(R, eng, golden, monkeypatch):
+    """The 32-bit modular-key kernel is the default; the double-carried integer key kernel stays as the
+    fallback (forced here through RSD_LONG_WIDE, and reached naturally by costs too large for the 32-bit bound)."""
+    rng = np.random.default_rng(77)
+    a = rng.integers(0, 4, size=2600, dtype=np.uint8)
+    b = mutate_codes(rng, a)
+    costs = golden["default_costs"]
+    eng.set_costs(costs)
+    ops, oi, oj, d = O.canonical_script(O.decode(a), O.decode(b), costs)
+    fast = eng.long_pair(a, b)
+    monkeypatch.setenv("RSD_LONG_WIDE", "1")
+    wide = eng.long_pair(a, b)
+    monkeypatch.delenv("RSD_LONG_WIDE")
+    for res in (fast, wide):
+        assert res["mode"] == 2 and res["dist"] == d
+        assert np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
+    # integer costs in the thousands: (32 * maxc + 64) << S exceeds 2^30 -> the wide kernel is chosen by the library
+    big = {"insert": 3000.0, "delete": 2500.0,
+           "update": {x: {y: (0.0 if x == y else 4100.0 + 7 * ((ord(x) + 3 * ord(y)) % 11)) for y in "AGCUYRWSKMDVHBN"} for x in "AGCUYRWSKMDVHBN"}}
+    eng.set_costs(big)
+    ops, oi, oj, d = O.canonical_script(O.decode(a), O.decode(b), big)
+    res = eng.long_pair(a, b)
+    assert res["mode"] == 2 and res["dist"] == d
+    assert np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)

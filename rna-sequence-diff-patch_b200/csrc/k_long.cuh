@@ -336,10 +336,14 @@ k_long_fwd32(LongArgs la, const IntCosts *__restrict__ icp) {
                 last = left; prev_recv = recv;
                 if ((i & 15) == 15 || i == m - 1) {
                     const int sh = 2 * (15 - (i & 15));
-                    uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
+                    if constexpr (C >= 4) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(i >> 4) * la.n_pad);
 #pragma unroll
-                    for (int c = 0; c < C; c += 4)
-                        dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
+                        for (int c = 0; c < C; c += 4)
+                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
+                    } else {
+                        *reinterpret_cast<uint2 *>(dcol + (size_t)(i >> 4) * la.n_pad) = make_uint2(acc[0] << sh, acc[1] << sh);
+                    }
                 }
             }
             if (lane == 31) s_pub[k] = last;

@@ -72,7 +72,14 @@ def c3(eng, n_pairs, reps=3):
             ts.append(time.perf_counter() - t0); kms.append(eng.last_kernel_ms())
     assert ok.all()
     t, k = float(np.mean(ts)), float(np.mean(kms)) * 1e-3
-    return {"config": "C3", "pairs": n_pairs, "cells": cells, "mode": mode.value,
+    # HBM streams of the script path: 2-bit direction codes written once by the forward kernel (16 rows per
+    # 32-bit word, columns padded to the 32-column strips), packed inputs read, op bytes written
+    la_, lb_ = np.diff(oa), np.diff(ob)
+    dir_bytes = float((((la_ + 15) // 16) * (((lb_ + 31) // 32) * 32) * 4).sum())
+    in_bytes = float(A.words.nbytes + B.words.nbytes + 2 * n_pairs * 12)
+    hbm = {"direction_bytes_written": dir_bytes, "packed_input_bytes": in_bytes, "op_bytes_written": float(n_ops.sum()),
+           "achieved_gbs_over_device_time": (dir_bytes + in_bytes + float(n_ops.sum())) / k * 1e-9, "peak_gbs": 6552.6}
+    return {"config": "C3", "hbm_streams": hbm, "pairs": n_pairs, "cells": cells, "mode": mode.value,
             "e2e_pairs_per_s": n_pairs / t, "e2e_gcups": cells / t * 1e-9, "e2e_s": t,
             "device_pairs_per_s": n_pairs / k, "device_gcups": cells / k * 1e-9, "device_s": k,
             "roundtrip_ok": bool(ok.all()), "output": "op bytes + n_ops + dist + ok (oi/oj derivable by prefix sum)"}

@@ -56,15 +56,38 @@ def gen_pairs(n_pairs: int, seed: int, alphabet_size: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe; NVML in-process, nvidia-smi as fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.via = "nvidia-smi"
+
+    def _nvml(self):
+        """The same NVML fields nvidia-smi prints, read in-process: a 35 ms timed region gets dozens of samples
+        instead of the one a 50 ms nvidia-smi call can deliver."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        bits = [pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                pynvml.nvmlClocksThrottleReasonSwPowerCap]
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        self.via = "nvml (in-process, 2 ms period)"
+        while not self.stop_flag.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            self.stop_flag.wait(0.002)
 
     def run(self):
+        try:
+            self._nvml()
+            return
+        except Exception:  # noqa: BLE001  (no pynvml / NVML error: fall back to the nvidia-smi recipe)
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -80,7 +103,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "via": self.via}
 
 
 def cpu_baseline(ca, oa, cb, ob, costs, target_s=12.0, nthreads=0):

@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(128)
 k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict__ out,
               uint32_t *__restrict__ scratch, int scratch_stride, uint32_t one) {
     static_assert(C % 16 == 0, "strip width must be a multiple of the 2-bit word");
-    __shared__ __align__(16) uint32_t s_tab[4];
-    if (threadIdx.x < 4) s_tab[threadIdx.x] = ic.rowtab4[threadIdx.x];
+    __shared__ __align__(32) uint32_t s_tab[8];          // [0..3] v[a][.], [4..7] the transposed table (swapped pairs)
+    if (threadIdx.x < 8) s_tab[threadIdx.x] = ic.rowtab4[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int n_tasks = pv.totals[1];
@@ -53,17 +53,25 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
         int ns = tt.ns, P = tt.P;
         if (ns == 0) {                               // class of long pairs: one group, shape from the pair
             const int p0 = pv.groups[tt.gfirst].x;
-            ns = (B.len[p0] + C - 1) / C; P = (ns + 31) >> 5;
+            const int m0 = A.len[p0], n0 = B.len[p0];
+            ns = ((plan_swap(m0, n0, C) ? m0 : n0) + C - 1) / C; P = (ns + 31) >> 5;
         }
 
         for (int pass = 0; pass < P; ++pass) {
             const LaneSlot ls = tape_slot(pv, tt, ns, pass, lane);
-            int m = 0, nA = 0, nB = 0;
+            // rows / columns after the orientation choice of the plan (plan_swap): the twins share m
+            int m = 0, nA = 0, nB = 0, baseA = 0, baseB = 0;
             const uint32_t *awA = A.words, *awB = A.words, *bwA = B.words, *bwB = B.words;
+            uint32_t sbaseA = sbase, sbaseB = sbase;
             if (ls.on) {
-                m = A.len[ls.pA]; nA = B.len[ls.pA]; nB = B.len[ls.pB];
+                const int mA = A.len[ls.pA], mB = A.len[ls.pB];
+                nA = B.len[ls.pA]; nB = B.len[ls.pB];
+                baseA = mA * ic.del + nA * ic.ins; baseB = mB * ic.del + nB * ic.ins;      // D = base - N either way
                 awA = A.words + A.start[ls.pA]; awB = A.words + A.start[ls.pB];
                 bwA = B.words + B.start[ls.pA]; bwB = B.words + B.start[ls.pB];
+                m = mA;
+                if (plan_swap(mA, nA, C)) { const uint32_t *t = awA; awA = bwA; bwA = t; m = nA; nA = mA; sbaseA = sbase + 16u; }
+                if (plan_swap(mB, nB, C)) { const uint32_t *t = awB; awB = bwB; bwB = t; nB = mB; sbaseB = sbase + 16u; }
             }
             const int col0 = ls.s * C;
             uint32_t sel[C];
@@ -115,8 +123,8 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                         const bool row_on = (unsigned)i < (unsigned)mrow;
                         if constexpr (HANDOFF) { if (ls.from_scratch && row_on) recv = scr_in[i]; }
                         uint32_t ra, rb;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sbase | (curA & 0xCu)));
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sbase | (curB & 0xCu)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sbaseA | (curA & 0xCu)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sbaseB | (curB & 0xCu)));
                         curA = __funnelshift_r(curA, curA, 2);
                         curB = __funnelshift_r(curB, curB, 2);
                         if (row_on) {
@@ -142,14 +150,14 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    out[ls.pA] = (double)(m * ic.del + nA * ic.ins - (int)(v & 0xffffu)) * inv_scale;
+                    out[ls.pA] = (double)(baseA - (int)(v & 0xffffu)) * inv_scale;
                 }
                 if (ls.hasB && ls.s == (nB - 1) / C) {
                     const int cl = (nB - 1) - ls.s * C;
                     uint32_t v = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (c == cl) v = H[c];
-                    out[ls.pB] = (double)(m * ic.del + nB * ic.ins - (int)(v >> 16)) * inv_scale;
+                    out[ls.pB] = (double)(baseB - (int)(v >> 16)) * inv_scale;
                 }
             }
             __syncwarp();

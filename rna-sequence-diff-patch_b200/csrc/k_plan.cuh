@@ -38,6 +38,13 @@ struct PlanView {
     unsigned long long *dbg;
 };
 
+// Twin plans may process a pair with the roles of the two sequences swapped (columns = the source): the
+// distance is the same number with ins/del exchanged and the substitution table transposed, and the
+// orientation with fewer strip-padding cells is taken: m * (n + pad(n))  vs  n * (m + pad(m)).
+__host__ __device__ __forceinline__ bool plan_swap(int m, int n, int C) {
+    const int pn = (n + C - 1) / C * C - n, pm = (m + C - 1) / C * C - m;
+    return (long long)n * pm < (long long)m * pn;
+}
 __host__ __device__ __forceinline__ int plan_nsq(int ns) { return ns > RSD_NSQ_MAX ? RSD_NSQ_MAX + 1 : ns; }
 __device__ __forceinline__ int plan_bin(int m, int n, const PlanView &pv) {
     const int nsq = plan_nsq((n + pv.C - 1) / pv.C);
@@ -79,6 +86,7 @@ __device__ __forceinline__ void plan_count_one(const int32_t *__restrict__ a_len
         if (out) out[p] = m == 0 ? __dmul_rn((double)n, ins) : __dmul_rn((double)m, del);
         return;
     }
+    if (pv.allow_twin && plan_swap(m, n, pv.C)) { const int t = m; m = n; n = t; }
     int bin = plan_bin(m, n, pv);
     pv.pair_bin[p] = bin;
     atomicAdd(&pv.bin_cnt[(size_t)((threadIdx.x >> 5) & (RSD_PLAN_COPIES - 1)) * RSD_NB_MAX + bin], 1);

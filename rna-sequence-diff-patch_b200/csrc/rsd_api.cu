@@ -193,13 +193,16 @@ int rsd_ctx::classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, 
         const int64_t pad_n = max_n + 64;
         const double bound = (double)max_m * ic.del + (double)pad_n * ic.ins + (double)maxabsw;
         i32_ok = bound < 2147483000.0;
-        i16_ok = bound < 65000.0;                                 // unsigned 16-bit N = -H'
+        // the int16x2 kernel may swap the roles of the two sequences: both orientations must fit
+        const double bound_sw = (double)max_n * ic.ins + (double)(max_m + 64) * ic.del + (double)maxabsw;
+        i16_ok = std::max(bound, bound_sw) < 65000.0;             // unsigned 16-bit N = -H'
         fast_ok = i16_ok && w8 && bits == 2 && (symmask & ~0xFu) == 0;
         if (fast_ok)
             for (int a = 0; a < 4; ++a) {
                 uint32_t r = 0;
-                for (int b = 0; b < 4; ++b) r |= (uint32_t)std::max(0, -ic.w[a][b]) << (8 * b);
-                ic.rowtab4[a] = r;
+                uint32_t rt = 0;
+                for (int b = 0; b < 4; ++b) { r |= (uint32_t)std::max(0, -ic.w[a][b]) << (8 * b); rt |= (uint32_t)std::max(0, -ic.w[b][a]) << (8 * b); }
+                ic.rowtab4[a] = r; ic.rowtab4[4 + a] = rt;
             }
     }
     int mode;
@@ -302,6 +305,7 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     RSD_OK_OR_RETURN(sl.bins.ensure(sizeof(int) * plan_ints));
     // twins need identical m; otherwise a task may mix pairs whose m differ a little (every lane keeps its
     // own row count), so rows are binned ~3 % of max_m at a time and sparse shapes still fill their tapes
+    if (allow_twin) max_m = max_n = std::max(max_m, max_n);                      // either sequence may end up as the rows (plan_swap)
     int lg = 0;
     while (((int64_t)2 << lg) <= std::max<int64_t>(max_m, 1)) ++lg;              // floor(log2(max_m))
     pv.m_shift = allow_twin ? 0 : std::min(std::max(lg - 5, 0), 6);
@@ -363,7 +367,7 @@ int rsd_ctx::distance_plan(const int32_t *a_len, const int32_t *b_len, int64_t n
     RSD_OK_OR_RETURN(classify(symmask, max_m, max_n, bits, force_mode, sl.mi));
     if (mode_out) *mode_out = sl.mi.mode;
     timed = false; last_ms_override = 0.0;
-    sl.n_pairs = n_pairs;
+    sl.n_pairs = n_pairs; sl.max_n = max_n;
     if (n_pairs == 0) return RSD_OK;
     if (!costs_preloaded) RSD_OK_OR_RETURN(upload_costs(sl.mi, st));
     const int C = sl.mi.mode == RSD_MODE_F64 ? 16 : 32;
@@ -384,9 +388,10 @@ int rsd_ctx::distance_launch(const uint32_t *a_words, const int64_t *a_start, co
     const int stride = (int)max_m;           // two boundary columns of max_m rows per warp (tape passes)
     if (mi.mode == RSD_MODE_I16X2) {
         RSD_OK_OR_RETURN(persistent_grid(k_dist_twin16<32>, THREADS, sm_count, blocks));
-        RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(uint32_t) * 2 * (size_t)stride * blocks * wpb + 16));
+        const int stride2 = (int)std::max<int64_t>(max_m, sl.max_n);     // rows after the orientation choice
+        RSD_OK_OR_RETURN(sl.scratch.ensure(sizeof(uint32_t) * 2 * (size_t)stride2 * blocks * wpb + 16));
         if (timing) RSD_CUDA(cudaEventRecord(cur_ev0, st));
-        k_dist_twin16<32><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)sl.scratch.p, stride, 1u);
+        k_dist_twin16<32><<<blocks, THREADS, 0, st>>>(pv, A, B, mi.ic, d_out, (uint32_t *)sl.scratch.p, stride2, 1u);
     } else if (mi.mode == RSD_MODE_I32) {
         if (bits == 2) {
             RSD_OK_OR_RETURN(persistent_grid(k_dist_gen<int, 2, 32>, THREADS, sm_count, blocks));

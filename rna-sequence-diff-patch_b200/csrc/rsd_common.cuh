@@ -17,7 +17,8 @@ struct IntCosts {
     int32_t ins, del;        // scaled by 2^k
     int32_t w[16][16];       // w[a][b] = sub(a,b) - ins - del (scaled); w[a][a] = -(ins+del)
     int32_t scale_log2;      // k
-    uint32_t rowtab4[4];     // 2-bit fast path: byte b of rowtab4[a] = v[a][b] = max(0, -w[a][b]) (<= 127)
+    uint32_t rowtab4[8];     // 2-bit fast path: byte b of rowtab4[a] = v[a][b] = max(0, -w[a][b]) (<= 127);
+                             // rowtab4[4 + a] holds the transposed table v[b][a] for pairs processed with swapped roles
 };
 struct F64Costs {
     double ins, del;

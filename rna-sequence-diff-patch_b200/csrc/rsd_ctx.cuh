@@ -66,7 +66,7 @@ struct PlanSlot {
     bool dirty = true;           // bin counters need a memset before the next plan
     PlanView pv;
     ModeInfo mi;
-    int64_t n_pairs = 0;
+    int64_t n_pairs = 0, max_n = 0;
     void release() { scratch.release(); pair_bin.release(); bins.release(); groups.release(); dirty = true; }
 };
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measure BASELINE configs 3, 4 and 5 (bench.py covers config 2, the headline).  One JSON line per
 config on stdout; used for profiles/ and DESIGN.md, not by the driver.
-    python tools/bench_configs.py [--c3-pairs N] [--c5-records N] [--which c3,c4,c5]"""
+    python tools/bench_configs.py [--c3-pairs N] [--c5-records N] [--which c3,c4,c5[,c5i]]   (c5i: C5 with 1 % IUPAC records, fp64)"""
 import argparse
 import json
 import os
@@ -110,12 +110,15 @@ def c4(eng, L=50000, reps=3):
             "device_gcups": cells / k * 1e-9, "device_s": k}
 
 
-def c5(eng, n_rec, nq=64, k=10, reps=3):
+def c5(eng, n_rec, nq=64, k=10, reps=3, iupac=False):
     rng = np.random.default_rng(20260005)
     lens = rng.integers(24, 32, size=n_rec)
     off = np.zeros(n_rec + 1, np.int64); np.cumsum(lens, out=off[1:])
     codes = rng.integers(0, 4, size=int(off[-1]), dtype=np.uint8)
     codes[rng.random(codes.shape[0]) < 1e-3] = 14
+    if iupac:                                           # second run, 1 % of the records drawn from all 15 symbols
+        full = np.repeat(rng.random(n_rec) < 0.01, lens)   #   -> non-dyadic default costs (0.66 / 0.83) -> fp64 reference-order kernels
+        codes[full] = rng.integers(0, 15, size=int(full.sum()), dtype=np.uint8)
     qs, qo = [], [0]
     for r in rng.integers(0, n_rec, size=nq):
         s = codes[off[r]:off[r + 1]].copy()
@@ -136,6 +139,11 @@ def c5(eng, n_rec, nq=64, k=10, reps=3):
             ts.append(time.perf_counter() - t0); kms.append(eng.last_kernel_ms())
     # the other scorers of search_collection on the same database (8f rank 4): one query, all scores + top-k on device
     sim = {}
+    if iupac:
+        eng.db_free()
+        t, kk = float(np.mean(ts)), float(np.mean(kms)) * 1e-3
+        return {"config": "C5-iupac", "records": n_rec, "queries": nq, "k": k, "cells": cells, "mode": eng.last_mode,
+                "e2e_gcups": cells / t * 1e-9, "e2e_s": t, "device_gcups": cells / kk * 1e-9, "device_s": kk}
     db_bytes = float(db.words.nbytes + n_rec * (8 + 4 + 8 + 8))           # words + start + len + perm read, score written
     for method in ("set_jaccard_similarity", "multi_dice_similarity", "cosine", "pearson"):
         ms = []
@@ -157,10 +165,12 @@ if __name__ == "__main__":
     ap.add_argument("--which", default="c3,c4,c5")
     ap.add_argument("--c3-pairs", type=int, default=100000)
     ap.add_argument("--c5-records", type=int, default=10_000_000)
+    ap.add_argument("--c5-iupac-queries", type=int, default=8)
     args = ap.parse_args()
     eng = R.Engine(0)
     for w in args.which.split(","):
         t0 = time.perf_counter()
-        res = {"c3": lambda: c3(eng, args.c3_pairs), "c4": lambda: c4(eng), "c5": lambda: c5(eng, args.c5_records)}[w]()
+        res = {"c3": lambda: c3(eng, args.c3_pairs), "c4": lambda: c4(eng), "c5": lambda: c5(eng, args.c5_records),
+               "c5i": lambda: c5(eng, args.c5_records, nq=args.c5_iupac_queries, reps=2, iupac=True)}[w]()
         res["wall_incl_datagen_s"] = time.perf_counter() - t0
         print(json.dumps(res), flush=True)

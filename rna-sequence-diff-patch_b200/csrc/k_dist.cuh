@@ -171,7 +171,7 @@ k_dist_twin16(PlanView pv, SeqView A, SeqView B, IntCosts ic, double *__restrict
 // products SED:159,177; no FMA contraction — every add/mul is an explicit _rn intrinsic).
 // =============================================================================================
 template <typename T, int BITS, int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? 5 : 4))
 k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
            const F64Costs *__restrict__ fcp, double *__restrict__ out,
            T *__restrict__ scratch, int scratch_stride) {
@@ -273,7 +273,10 @@ k_dist_gen(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp,
                             const double c1 = __dadd_rn(H[c], c_del);      // SED:97
                             const double c2 = __dadd_rn(diag, w);          // SED:99
                             diag = H[c];
-                            H[c] = dmin2(dmin2(c0, c1), c2);               // SED:106-107
+                            // SED:106-107 min(c0, c1, c2): the value of a min does not depend on the association, so
+                            // the two candidates that do not involve the left neighbour are combined first and only
+                            // DADD + one compare-select sit on the row's dependency chain
+                            H[c] = dmin2(c0, dmin2(c1, c2));
                         } else {
                             const int t2 = addmin32(diag, w, H[c]);
                             diag = H[c];

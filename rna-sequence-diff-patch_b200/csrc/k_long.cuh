@@ -165,7 +165,7 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
                     if constexpr (F64) {
                         const double c0 = __dadd_rn(left, c_ins), c1 = __dadd_rn(H[c], c_del), c2 = __dadd_rn(diag, wv);
                         const int s0 = left_s + 1, s1 = HS[c] + 1, s2 = diag_s + 1;
-                        const double v = dmin2(dmin2(c0, c1), c2);
+                        const double v = dmin2(c0, dmin2(c1, c2));         // same value; only one compare-select after left + ins
                         int bs = (c0 == v) ? s0 : 0x7fffffff; code = 0u;
                         if (c1 == v && s1 < bs) { bs = s1; code = 1u; }
                         if (c2 == v && s2 < bs) { bs = s2; code = 2u; }

@@ -160,7 +160,7 @@ k_script_fwd(PlanView pv, SeqView A, SeqView B, const IntCosts *__restrict__ icp
                             const double c1 = __dadd_rn(H[c], c_del);
                             const double c2 = __dadd_rn(diag, w);
                             const int s0 = left_s + 1, s1 = HS[c] + 1, s2 = diag_s + 1;
-                            const double v = dmin2(dmin2(c0, c1), c2);
+                            const double v = dmin2(c0, dmin2(c1, c2));         // same value; only one compare-select after left + ins
                             int bs = (c0 == v) ? s0 : 0x7fffffff; code = 0u;
                             if (c1 == v && s1 < bs) { bs = s1; code = 1u; }
                             if (c2 == v && s2 < bs) { bs = s2; code = 2u; }

@@ -370,6 +370,168 @@ k_long_fwd32(LongArgs la, const IntCosts *__restrict__ icp) {
     }
 }
 
+// Same keys and protocol as k_long_fwd32, but every lane advances TWO rows per step (a 2 x C register tile):
+// one loop overhead, one pair of shuffles and one boundary exchange per two rows, and the two rows form a
+// small wavefront (cell (r+1, c) needs (r, c), (r, c-1), (r+1, c-1)) that gives the single resident warp
+// independent instructions to issue.  Lane l works on rows 2(s - l), 2(s - l) + 1 at step s; blocks are 16
+// steps = 32 rows, so the boundary exchange moves 32 rows at a time (one per lane).
+template <int C>
+__global__ void __launch_bounds__(32)
+k_long_fwd32x2(LongArgs la, const IntCosts *__restrict__ icp) {
+    __shared__ uint32_t s_w[256];
+    __shared__ uint32_t s_pub[32];
+    __shared__ __align__(4) uint8_t s_a[96];
+    for (int k = threadIdx.x; k < 256; k += 32)
+        s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << la.S) - 1);
+    __syncwarp();
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x;
+    const int m = la.m, n = la.n;
+    const int col0 = (w * 32 + lane) * C;
+    const bool strip_on = col0 < n;
+    uint32_t H[C], acc[C], bca[C];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int bc = (col0 + c < n) ? la.b[col0 + c] : 0;
+        H[c] = 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc;
+    }
+    uint32_t last0 = 0u, last1 = 0u, prev_recv1 = 0u;       // last column of the two rows of the previous step; recv1 of the previous step
+    long long full = 0;
+    const unsigned long long *bin = w > 0 ? (const unsigned long long *)la.bound + (size_t)(w - 1) * m : nullptr;
+    unsigned long long *bout = (unsigned long long *)la.bound + (size_t)w * m;
+    const bool publish = (w + 1 < la.n_panels);
+    uint32_t *dcol = la.dirs + col0;
+    const int steps = (m + 1) / 2 + 31 + 16;        // + one block so the last rows get published
+    // source symbols of a block: rows 2(t0 - 31) .. 2(t0 + 15) + 1 (94 rows), three per lane, fetched one block ahead
+    auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)m) ? la.a[r] : (uint8_t)0; };
+    uint8_t pf0 = fetch(0, 0), pf1 = fetch(0, 1), pf2 = fetch(0, 2);
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += 16) {
+        const uint32_t last_at_block_start = last1;
+        if (publish) {
+            const int r = 2 * (t0 - 47) + lane;
+            if (r >= 0 && r < m) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
+        }
+        __syncwarp();
+        uint32_t bval = 0u;
+        if (w > 0) {
+            const bool mine = 2 * t0 + lane < m;
+            unsigned long long raw = 0ull;
+            do {
+                if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
+            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));      // warp-uniform exit (see k_long_fwd)
+            bval = (uint32_t)raw;
+        }
+        // codes0 / codes1: 16 nibbles each = the table rows of this lane's first / second row in the 16 steps
+        unsigned long long codes0 = 0ull, codes1 = 0ull;
+        {
+            s_a[lane] = pf0; s_a[32 + lane] = pf1; s_a[64 + lane] = pf2;
+            pf0 = fetch(t0 + 16, 0); pf1 = fetch(t0 + 16, 1); pf2 = fetch(t0 + 16, 2);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t two = *reinterpret_cast<const uint16_t *>(s_a + 2 * (31 - lane + k));
+                codes0 |= (unsigned long long)(two & 15u) << (4 * k);
+                codes1 |= (unsigned long long)((two >> 8) & 15u) << (4 * k);
+            }
+            __syncwarp();
+        }
+        auto run16 = [&](auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const int i0 = 2 * (t0 + k - lane);
+            const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)m);
+            const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)m);
+            const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) << 6, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) << 6;
+            uint32_t w0[C], w1[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0[c]) : "r"(bca[c] + off0));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[c]) : "r"(bca[c] + off1));
+            }
+            // first row, the part that does not involve the left neighbour
+            uint32_t t2a[C]; int e1a[C];
+            {
+                uint32_t diag = prev_recv1;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t up = H[c];
+                    const uint32_t x = diag + w0[c];
+                    e1a[c] = (int)(x - up);
+                    t2a[c] = up + (uint32_t)min(e1a[c], 0);
+                    diag = up;
+                }
+            }
+            uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
+            uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
+            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, 2 * k), b1 = __shfl_sync(RSD_FULL, bval, 2 * k + 1);
+            if (lane == 0) { recv0 = w > 0 ? b0 : 0u; recv1 = w > 0 ? b1 : 0u; }
+            if (on0) {
+                uint32_t left = recv0, h0[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int e2 = (int)(t2a[c] - left);
+                    h0[c] = t2a[c] + (uint32_t)__viaddmin_s32((int)left, -(int)t2a[c], 0);
+                    left = h0[c];
+                    acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
+                    acc[c] = __funnelshift_l((uint32_t)e1a[c], acc[c], 1);
+                }
+                last0 = left;
+                if (on1) {
+                    uint32_t diag = recv0, left1 = recv1;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const uint32_t up = h0[c];
+                        const uint32_t x = diag + w1[c];
+                        const int e1 = (int)(x - up);
+                        const uint32_t t2 = up + (uint32_t)min(e1, 0);
+                        const int e2 = (int)(t2 - left1);
+                        const uint32_t hn = t2 + (uint32_t)__viaddmin_s32((int)left1, -(int)t2, 0);
+                        diag = up; H[c] = hn; left1 = hn;
+                        acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
+                        acc[c] = __funnelshift_l((uint32_t)e1, acc[c], 1);
+                    }
+                    last1 = left1;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) H[c] = h0[c];
+                    last1 = last0;                              // the panel's running last column (only used for the key tracking)
+                }
+                prev_recv1 = recv1;
+                const int il = on1 ? i0 + 1 : i0;               // last row done in this step
+                if ((il & 15) == 15 || il == m - 1) {
+                    const int sh = 2 * (15 - (il & 15));
+                    if constexpr (C >= 4) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(il >> 4) * la.n_pad);
+#pragma unroll
+                        for (int c = 0; c < C; c += 4)
+                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
+                    } else {
+                        *reinterpret_cast<uint2 *>(dcol + (size_t)(il >> 4) * la.n_pad) = make_uint2(acc[0] << sh, acc[1] << sh);
+                    }
+                }
+            }
+            if (lane == 31) { s_pub[2 * k] = last0; s_pub[2 * k + 1] = last1; }
+        }
+        };
+        if (2 * (t0 - 31) >= 0 && 2 * (t0 + 15) + 1 <= m - 1) run16(std::true_type{}); else run16(std::false_type{});
+        __syncwarp();
+        full += (long long)(int)(last1 - last_at_block_start);          // <= 32 bounded row-to-row differences (host check)
+    }
+    if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
+        const int cl = (n - 1) - col0;
+        uint32_t res = 0u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
+        const long long hkey = full + (long long)(int)(res - H[C - 1]);
+        const long long key = hkey + (long long)m * (((long long)icp->del << la.S) + 1) + (long long)n * (((long long)icp->ins << la.S) + 1);
+        la.dist[0] = (double)(key >> la.S) / (double)(1 << icp->scale_log2);
+    }
+}
+
 // Traceback of the long pair: one warp.  The walk is a chain of ~m+n dependent reads, so the warp
 // stages a 64-row x 64-column tile of direction words around the current cell in shared memory with
 // coalesced loads, the warp walks inside the tile (whole diagonal runs per iteration, shared-memory

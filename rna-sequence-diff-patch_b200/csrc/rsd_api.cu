@@ -1236,18 +1236,20 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
         long long maxc = std::max<long long>(mi.ic.ins, mi.ic.del);
         for (int x = 0; x < 16; ++x) for (int y = 0; y < 16; ++y)
             if ((symmask >> x & 1) && (symmask >> y & 1)) maxc = std::max<long long>(maxc, std::llabs((long long)mi.ic.w[x][y]));
-        key32_ok = S <= 24 && ((32 * maxc + 64) << S) < (1ll << 30);     // covers 16 rows of drift (the per-block key tracking)
+        key32_ok = S <= 24 && ((64 * maxc + 128) << S) < (1ll << 30);    // covers 32 rows of drift (the per-block key tracking)
     }
     // 4 columns per lane: the forward pass is latency-bound (one warp per panel, a dependent chain per
     // row), so narrow panels = more panels in flight win until the panel pipeline lag dominates
-    // (measured at 50 kb, 32-bit keys: C=2 12.8 ms, C=4 10.5 ms, C=8 10.9 ms, C=16 13.6 ms; double-carried keys: 15.4 / 22.8 / 19.9 ms).
+    // (measured at 50 kb, 32-bit keys, two rows per step: C=2 11.5 ms, C=4 7.8 ms, C=8 8.3 ms; one row per step: 12.8 / 10.5 / 10.9 ms; double-carried keys: 15.4 / 22.8 / 19.9 ms).
     int C = 4;
     if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || (v == 2 && key32_ok)) C = v; }
     const int n_panels = (int)((n + 32 * C - 1) / (32 * C));
     const int64_t n_pad = (int64_t)n_panels * 32 * C;
     int per_sm = 0;
     const bool key32 = key32_ok;
-    const void *kfn = key32 ? (C == 2 ? (const void *)k_long_fwd32<2> : C == 4 ? (const void *)k_long_fwd32<4> : C == 16 ? (const void *)k_long_fwd32<16> : (const void *)k_long_fwd32<8>) :
+    const bool two_rows = key32 && !getenv("RSD_LONG_R1");      // 2 x C register tile per step (default) or one row per step
+    const void *kfn = two_rows ? (C == 2 ? (const void *)k_long_fwd32x2<2> : C == 4 ? (const void *)k_long_fwd32x2<4> : C == 16 ? (const void *)k_long_fwd32x2<16> : (const void *)k_long_fwd32x2<8>) :
+                      key32 ? (C == 2 ? (const void *)k_long_fwd32<2> : C == 4 ? (const void *)k_long_fwd32<4> : C == 16 ? (const void *)k_long_fwd32<16> : (const void *)k_long_fwd32<8>) :
                       f64 ? (C == 4 ? (const void *)k_long_fwd<true, 4> : C == 16 ? (const void *)k_long_fwd<true, 16> : (const void *)k_long_fwd<true, 8>)
                           : (C == 4 ? (const void *)k_long_fwd<false, 4> : C == 16 ? (const void *)k_long_fwd<false, 16> : (const void *)k_long_fwd<false, 8>);
     RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32, 0));

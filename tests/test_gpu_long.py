@@ -113,7 +113,10 @@ def test_wide_key_fallback_paths_agree(R, eng, golden, monkeypatch):
     monkeypatch.setenv("RSD_LONG_WIDE", "1")
     wide = eng.long_pair(a, b)
     monkeypatch.delenv("RSD_LONG_WIDE")
-    for res in (fast, wide):
+    monkeypatch.setenv("RSD_LONG_R1", "1")                      # 32-bit keys, one row per step
+    one_row = eng.long_pair(a, b)
+    monkeypatch.delenv("RSD_LONG_R1")
+    for res in (fast, wide, one_row):
         assert res["mode"] == 2 and res["dist"] == d
         assert np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
     # integer costs in the thousands: (32 * maxc + 64) << S exceeds 2^30 -> the wide kernel is chosen by the library

@@ -539,7 +539,7 @@ k_long_fwd32x2(LongArgs la, const IntCosts *__restrict__ icp) {
 // end of tmp[0 .. m+n).
 __global__ void __launch_bounds__(32) k_long_traceback(int m, int n, const uint32_t *__restrict__ dirs, int n_pad,
                                                        uint8_t *__restrict__ tmp, int32_t *__restrict__ n_ops) {
-    constexpr int TR = 4, TC = 64;                 // row blocks (16 rows each) x columns per tile
+    constexpr int TR = 16, TC = 256;               // row blocks (16 rows each) x columns per tile
     __shared__ uint32_t tile[TR][TC];
     const int lane = threadIdx.x;
     int i = m, j = n;

@@ -194,19 +194,11 @@ struct TapeTask {
     int ng;            // groups in this task
 };
 
-// Called by all 32 lanes of a converged warp: the bin of ticket W = largest b with bin_warp_off[b] <= W, found
-// by a 32-way search (every lane probes one position per round; 3 rounds for ~3000 bins instead of the 12
-// dependent loads of a binary search — this sits on the critical path of every task start).
 __device__ __forceinline__ TapeTask plan_decode(const PlanView &pv, int W) {
-    const int lane = threadIdx.x & 31;
-    int lo = 0, hi = pv.NB;                        // bin_warp_off[lo] <= W < bin_warp_off[hi]
+    int lo = 0, hi = pv.NB;                        // largest b with bin_warp_off[b] <= W
     while (hi - lo > 1) {
-        const int pos = lo + (int)(((long long)(hi - lo) * (lane + 1)) / 33);      // non-decreasing in lane, inside [lo, hi)
-        const unsigned le = __ballot_sync(RSD_FULL, __ldg(&pv.bin_warp_off[pos]) <= W);   // monotone: 1..1 0..0
-        const int k = __popc(le);
-        const int below = __shfl_sync(RSD_FULL, pos, max(k - 1, 0)), above = __shfl_sync(RSD_FULL, pos, min(k, 31));
-        if (k > 0) lo = below;
-        if (k < 32) hi = above;
+        int mid = (lo + hi) >> 1;
+        if (__ldg(&pv.bin_warp_off[mid]) <= W) lo = mid; else hi = mid;
     }
     const int b = lo;
     const int nsq = bin_nsq(b, pv);

@@ -24,6 +24,14 @@ __device__ __forceinline__ uint32_t ub_op(uint32_t x, uint32_t y, uint32_t z) {
         return (uint32_t)__vimin3_s32((int)x, (int)y, (int)z);
     } else if constexpr (WHICH == 8) {     // VIMNMX.S16x2 two-input form used by the kernels
         return __vimin3_s16x2(x, y, y);
+    } else if constexpr (WHICH == 9) {     // IMAD.HI.U32
+        uint32_t r; asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
+        return r;
+    } else if constexpr (WHICH == 10) {    // IMAD.WIDE.U32 (64-bit product, low half fed back)
+        unsigned long long r; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(x), "r"(y));
+        return (uint32_t)r ^ (uint32_t)(r >> 32);
+    } else if constexpr (WHICH == 11) {    // SHF (funnel shift, as used for the direction bits)
+        return __funnelshift_l(y, x, 1);
     } else {
         return x;
     }

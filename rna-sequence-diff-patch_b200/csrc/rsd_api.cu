@@ -662,6 +662,9 @@ extern "C" int rsd_ubench(rsd_ctx *c, int which, double *ops_per_s) {
             case 6: k_ubench_u32<6><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
             case 7: k_ubench_mix<<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
             case 8: k_ubench_u32<8><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 9: k_ubench_u32<9><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 10: k_ubench_u32<10><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
+            case 11: k_ubench_u32<11><<<blocks, threads, 0, st>>>(iters, y, z, (uint32_t *)c->ps().scratch.p); break;
             default: return rsd_fail(RSD_EINVAL, "rsd_ubench: unknown kind %d", which);
         }
         RSD_CUDA(cudaEventRecord(c->ev1, st));

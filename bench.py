@@ -170,7 +170,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "user_costs.json")))
+    costs = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
     alpha = 4 if args.workload == "c2" else 15
     config = {"workload": f"C2: {args.pairs} pairs/GPU, len U[100,300], "
                           f"{'ACGU (2-bit)' if alpha == 4 else '15-letter IUPAC (4-bit)'}, user_costs.json, distance only",

@@ -2,8 +2,8 @@
 
 Same names, argument meaning and error behaviour as /root/reference/StringEditDistance.py; the
 matrix fill runs on the GPU through librsd.so.  Like the reference (SED:6-18) the cost files are
-read from the current working directory at import; when costs.json is absent there, the copy
-shipped next to this file is used.  The reference's import-time self-test print (SED:463-471) is
+read from the current working directory at import; when a file is absent there, the same table
+built into the package (cost_tables.py) is used.  The reference's import-time self-test print (SED:463-471) is
 not reproduced: call selftest()."""
 import json
 import os
@@ -18,19 +18,18 @@ from rna_sequence_diff_patch_b200 import sed as _sed  # noqa: E402
 from rna_sequence_diff_patch_b200.sed import Edge, Node  # noqa: E402,F401
 
 
-def _open_cost_file(name):
-    return open(name, "r") if os.path.exists(name) else open(os.path.join(_HERE, name), "r")
+from rna_sequence_diff_patch_b200 import cost_tables as _tables  # noqa: E402
 
 
-with _open_cost_file("costs.json") as f:
-    default_costs = json.load(f)
+def _load_cost_file(name, builtin):
+    if os.path.exists(name):
+        with open(name, "r") as f:
+            return json.load(f)
+    return builtin()
 
-try:
-    with _open_cost_file("user_costs.json") as f:
-        user_costs = json.load(f)
-except (OSError, IOError):
-    user_costs = default_costs
-    print('Could not find user costs file')
+
+default_costs = _load_cost_file("costs.json", _tables.default_costs)
+user_costs = _load_cost_file("user_costs.json", _tables.user_costs)
 
 
 def reload_user_costs():

@@ -38,7 +38,7 @@ def test_loads_without_gpu_and_fails_loudly(built):
     assert lib.rsd_abi_version() == 1
     if lib.rsd_device_count() == 0:
         eng = built.Engine(0)
-        eng.set_costs(json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "costs.json"))))
+        eng.set_costs(__import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs())
         p = built.pack(["ACGU", "GGA"])
         with pytest.raises(built.RsdError) as ei:
             eng.distance_batch(p, p)

@@ -16,7 +16,7 @@ def _worker(rank, world, port, tmp):
     from rna_sequence_diff_patch_b200.dist_search import shard_bounds, gather_merge
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "costs.json")))
+    costs = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
     rng = np.random.default_rng(5)
     n = 3001
     lens = rng.integers(24, 32, size=n)
@@ -86,7 +86,7 @@ def _pairs_worker(rank, world, port, tmp):
     from rna_sequence_diff_patch_b200.dist_pairs import ShardedPairs
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "user_costs.json")))
+    costs = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
     rng = np.random.default_rng(11)
     n = 501
     la = rng.integers(0, 60, size=n); lb = rng.integers(0, 60, size=n)

@@ -14,12 +14,16 @@ def all_cases(g):
     return [g["G1"]] + g["small"] + g["medium"] + list(g["xml_named"].values())
 
 
-def test_cost_files_match_reference_dicts(golden):
+def test_builtin_cost_tables_match_reference_files(golden, tmp_path):
+    """cost_tables.py == the dicts the reference loaded from its costs.json / user_costs.json (values, key order,
+    float typing), and write_cost_files() round-trips through the JSON format."""
     import json, os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    pkg = os.path.join(root, "rna-sequence-diff-patch_b200", "dropin")
-    assert json.load(open(os.path.join(pkg, "costs.json"))) == golden["default_costs"]
-    assert json.load(open(os.path.join(pkg, "user_costs.json"))) == golden["user_costs"]
+    from rna_sequence_diff_patch_b200 import cost_tables as T
+    assert json.dumps(T.DEFAULT_COSTS) == json.dumps(golden["default_costs"])
+    assert json.dumps(T.USER_COSTS) == json.dumps(golden["user_costs"])
+    T.write_cost_files(str(tmp_path))
+    assert json.load(open(os.path.join(str(tmp_path), "costs.json"))) == golden["default_costs"]
+    assert json.load(open(os.path.join(str(tmp_path), "user_costs.json"))) == golden["user_costs"]
 
 
 def test_distance_all_cases(golden):

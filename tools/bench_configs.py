@@ -18,7 +18,7 @@ G.build()
 import rna_sequence_diff_patch_b200 as R  # noqa: E402
 
 DROPIN = os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin")
-DEFAULT = json.load(open(os.path.join(DROPIN, "costs.json")))
+DEFAULT = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
 
 
 def mutate_batch(rng, codes, off, alpha=4, p_sub=0.05, p_ins=0.025, p_del=0.025, lo=1000, hi=2000):

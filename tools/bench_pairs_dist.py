@@ -49,7 +49,7 @@ def main():
     bounds = pair_shard_bounds(A.len, B.len, world)
     lo, hi = bounds[rank]
     a, b = slice_packed(A, lo, hi), slice_packed(B, lo, hi)
-    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "user_costs.json")))
+    costs = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
     eng = R.Engine(local); eng.set_costs(costs)
     lib = R.load_library()
     hp = [torch.from_numpy(x).pin_memory() for x in (a.words, a.start, a.len, b.words, b.start, b.len)]

@@ -59,7 +59,7 @@ def main():
     lo, hi = shard_bounds(lens, world)[rank]
     shard = R.pack((codes[off[lo]:off[hi]], (off[lo:hi + 1] - off[lo]).copy()), bits=4)
     shard.symmask |= 1 << 14
-    costs = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin", "costs.json")))
+    costs = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
     eng = R.Engine(local); eng.set_costs(costs)
     eng.db_load(shard, global_index_base=lo)
 

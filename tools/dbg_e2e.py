@@ -7,7 +7,7 @@ from rna_sequence_diff_patch_b200 import _lib
 import bench
 ca, oa, cb, ob = bench.gen_pairs(1_000_000, 20260002, 4)
 A = R.pack((ca, oa)); B = R.pack((cb, ob))
-eng = R.Engine(0); eng.set_costs(json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/user_costs.json"))))
+eng = R.Engine(0); eng.set_costs(__import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs())
 lib = R.load_library()
 def run(bufs, out, label, reps=5):
     ptr = lambda a, t: C.cast(a, C.POINTER(t))

@@ -2,7 +2,7 @@ import json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import rna_sequence_diff_patch_b200 as R
-eng = R.Engine(0); eng.set_costs(json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/costs.json")))); eng.set_timing(True)
+eng = R.Engine(0); eng.set_costs(__import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()); eng.set_timing(True)
 rng = np.random.default_rng(1)
 m = n = 50000
 a = rng.integers(0, 4, size=m, dtype=np.uint8); b = rng.integers(0, 4, size=n, dtype=np.uint8)

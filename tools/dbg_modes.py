@@ -4,8 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import __graft_entry__ as G; G.build()
 import rna_sequence_diff_patch_b200 as R
 import bench
-D = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/costs.json")))
-U = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/user_costs.json")))
+D = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
+U = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
 eng = R.Engine(0); eng.set_timing(True)
 n = 300000
 ca, oa, cb, ob = bench.gen_pairs(n, 1, 4)

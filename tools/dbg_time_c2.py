@@ -6,7 +6,7 @@ import rna_sequence_diff_patch_b200 as R
 import bench
 ca, oa, cb, ob = bench.gen_pairs(1_000_000, bench.SEEDS["c2"], 4)
 A = R.pack((ca, oa)); B = R.pack((cb, ob))
-eng = R.Engine(0); eng.set_costs(json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/user_costs.json")))); eng.set_timing(True)
+eng = R.Engine(0); eng.set_costs(__import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()); eng.set_timing(True)
 ms = []
 for r in range(6):
     eng.distance_batch(A, B)

@@ -22,8 +22,8 @@ import rna_sequence_diff_patch_b200 as R  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 DROPIN = os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin")
-DEFAULT = json.load(open(os.path.join(DROPIN, "costs.json")))
-USER = json.load(open(os.path.join(DROPIN, "user_costs.json")))
+DEFAULT = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
+USER = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
 SYM = "AGCUYRWSKMDVHBN"
 
 

@@ -8,8 +8,8 @@ import __graft_entry__ as G; G.build()
 import rna_sequence_diff_patch_b200 as R
 from oracle import oracle as O
 
-D = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/costs.json")))
-U = json.load(open(os.path.join(ROOT, "rna-sequence-diff-patch_b200/dropin/user_costs.json")))
+D = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
+U = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).user_costs()
 rng = np.random.default_rng(3)
 def seqs(n, lo, hi, al):
     al = np.array(list(al)); return ["".join(al[rng.integers(0, len(al), size=L)]) for L in rng.integers(lo, hi + 1, size=n)]

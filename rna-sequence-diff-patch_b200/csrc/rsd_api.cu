@@ -722,6 +722,9 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
                              int *mode_out) {
     cudaStream_t st = stream;
     last_ms_override = 0.0;
+    const bool trace = getenv("RSD_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_in = now();
     const int64_t max_m = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, a_len[i]); return (int64_t)v; }();
     const int64_t max_n = [&] { int32_t v = 0; for (int64_t i = 0; i < n_pairs; ++i) v = std::max(v, b_len[i]); return (int64_t)v; }();
     if (max_ops < max_m + max_n && n_pairs > 0) {
@@ -751,11 +754,19 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
     const int C = f64 ? 16 : 32;
 
     // per-pair direction-word counts and chunking
-    size_t free_b = 0, total_b = 0;
-    RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // The chunk budget is what the direction buffer already holds when that was sized by an earlier call with
+    // outputs of at least this size (cudaMemGetInfo costs ~15 ms with tens of GB allocated — measured); otherwise
+    // 70 % of the free memory, at most 24 GiB of direction words per chunk.
     const int64_t out_bytes = n_pairs * max_ops * (int64_t)((op ? 1 : 0) + (oi ? 4 : 0) + (oj ? 4 : 0)) + n_pairs * 32;
-    int64_t budget_words = ((int64_t)(free_b * 0.70) - out_bytes) / 4;
-    budget_words = std::min<int64_t>(budget_words, (int64_t)6 << 30);        // <= 24 GiB of direction words per chunk
+    int64_t budget_words;
+    if (dirs.p && dirs_budget_words > 0 && out_bytes <= dirs_budget_out_bytes) budget_words = dirs_budget_words;
+    else {
+        size_t free_b = 0, total_b = 0;
+        RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget_words = ((int64_t)((free_b + dirs.cap) * 0.70) - out_bytes) / 4;
+        budget_words = std::min<int64_t>(budget_words, (int64_t)6 << 30);
+        dirs_budget_words = budget_words; dirs_budget_out_bytes = out_bytes;
+    }
     std::vector<int64_t> dir_off((size_t)n_pairs);
     std::vector<int64_t> chunk_start; chunk_start.push_back(0);
     int64_t acc = 0, chunk_max_words = 0;
@@ -777,7 +788,8 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
     int64_t chunk_max_pairs = 0;
     for (size_t k = 0; k + 1 < chunk_start.size(); ++k) chunk_max_pairs = std::max(chunk_max_pairs, chunk_start[k + 1] - chunk_start[k]);
 
-    RSD_OK_OR_RETURN(dirs.ensure(sizeof(uint32_t) * (size_t)(chunk_max_words + 64)));
+    const double t_plan = now();
+    if (int rc = dirs.ensure(sizeof(uint32_t) * (size_t)(chunk_max_words + 64))) { dirs_budget_words = 0; return rc; }   // re-measure next time
     RSD_OK_OR_RETURN(misc.ensure(sizeof(int64_t) * (size_t)n_pairs));                      // dir_off
     RSD_OK_OR_RETURN(s_tmp.ensure((size_t)chunk_max_pairs * max_ops + 16));
     RSD_OK_OR_RETURN(s_nops.ensure(sizeof(int32_t) * (size_t)n_pairs));
@@ -834,6 +846,9 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         RSD_CUDA(cudaGetLastError());
     }
     if (timing) { RSD_CUDA(cudaEventRecord(ev1, st)); timed = true; }
+    const double t_enq = now();
+    if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[rsd trace] script: host prep %.3f ms, alloc+enqueue %.3f ms, kernels done after %.3f ms, %zu chunk(s)\n",
+                                                   t_plan - t_in, t_enq - t_plan, now() - t_in, chunk_start.size() - 1); }
     if (op) RSD_CUDA(cudaMemcpyAsync(op, s_op.p, (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
     if (oi) RSD_CUDA(cudaMemcpyAsync(oi, s_oi.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
     if (oj) RSD_CUDA(cudaMemcpyAsync(oj, s_oj.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
@@ -841,6 +856,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
     if (dist) RSD_CUDA(cudaMemcpyAsync(dist, out_f64.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     if (ok) RSD_CUDA(cudaMemcpyAsync(ok, s_ok.p, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     RSD_CUDA(cudaStreamSynchronize(st));
+    if (trace) fprintf(stderr, "[rsd trace] script: results on the host after %.3f ms\n", now() - t_in);
     return RSD_OK;
 }
 

@@ -96,6 +96,7 @@ struct rsd_ctx {
     PlanSlot &ps() { return slots[cur_slot]; }
     DevBuf mat_vals, mat_mask, mat_ab;
     // script / patch
+    int64_t dirs_budget_words = 0, dirs_budget_out_bytes = 0;     // chunk budget of the script path, measured once
     DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, s_tmp, p_out, p_len, p_err, misc;
     // database shard
     SeqBufs db;

@@ -25,7 +25,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("RSD_NVCC_EXTRA", "").split(), "-o", SO, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)

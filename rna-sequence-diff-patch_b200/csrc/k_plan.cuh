@@ -19,6 +19,9 @@
 #define RSD_NSQ_MAX 128                   // ns is binned exactly up to here; longer pairs share class NSQ_MAX+1
 #define RSD_NB_MAX ((RSD_NSQ_MAX + 2) * RSD_MQ_MAX)
 #define RSD_PLAN_COPIES 8                 // privatised bin counters: the L2 serialises atomics per address
+#ifndef RSD_TAPE_GAIN
+#define RSD_TAPE_GAIN 108                 // extra passes must buy this much utilisation (percent of the shortest layout)
+#endif
 
 struct PlanView {
     int *pair_bin;        // [n_pairs] bin of each pair, -1 = trivial (m == 0 or n == 0)
@@ -72,7 +75,7 @@ __host__ __device__ __forceinline__ void tape_shape(int nsq, int &P, int &G) {
         if ((long long)g * bp > (long long)bg * p) { bp = p; bg = g; }      // g/p > bg/bp
     }
     // utilisation ratio best/shortest = (bg/bp) / (g0/pmin) >= 1.08 ?
-    if ((long long)bg * pmin * 100 < (long long)g0 * bp * 108) { bp = pmin; bg = g0; }
+    if ((long long)bg * pmin * 100 < (long long)g0 * bp * RSD_TAPE_GAIN) { bp = pmin; bg = g0; }
     P = bp; G = bg;
 }
 

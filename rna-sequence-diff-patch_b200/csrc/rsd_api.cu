@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 #include <vector>
 #include <chrono>
 
@@ -258,26 +259,91 @@ extern "C" int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int
     if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd_pack: bits must be 2 or 4");
     const int per = 32 / bits;
     const uint32_t lim = 1u << bits;
+    // pass 1 (serial, cheap): lengths and word offsets
     int64_t w = 0;
-    uint32_t mask = 0;
     for (int64_t i = 0; i < n; ++i) {
         const int64_t L = off[i + 1] - off[i];
         if (L < 0 || L > INT32_MAX) return rsd_fail(RSD_EINVAL, "rsd_pack: bad offsets at sequence %lld", (long long)i);
         start[i] = w; len[i] = (int32_t)L;
-        const uint8_t *s = codes + off[i];
-        for (int64_t k = 0; k < L; k += per) {
-            uint32_t word = 0;
-            const int lim_k = (int)std::min<int64_t>(per, L - k);
-            for (int c = 0; c < lim_k; ++c) {
-                const uint32_t v = s[k + c];
-                if (v >= lim) return rsd_fail(RSD_EINVAL, "rsd_pack: code %u at sequence %lld does not fit %d bits", v, (long long)i, bits);
-                mask |= 1u << v;
-                word |= v << (bits * c);
-            }
-            words[w++] = word;
-        }
+        w += (L + per - 1) / per;
     }
-    for (int p = 0; p < 4; ++p) words[w++] = 0;
+    for (int p = 0; p < 4; ++p) words[w + p] = 0;
+    // pass 2: the packing itself, sequences split over the host threads (large batches only)
+    const int64_t total = n ? off[n] - off[0] : 0;
+    int n_thr = 1;
+    if (total >= (1 << 22)) n_thr = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    std::vector<uint32_t> masks((size_t)n_thr, 0u);
+    std::vector<int64_t> bad((size_t)n_thr, -1);
+    // eight symbols at a time: one 64-bit load, a range check on all bytes, and a shift-or cascade that squeezes
+    // the low `bits` of every byte together (2-bit: 8 symbols -> 16 bits, 4-bit: 8 symbols -> 32 bits)
+    auto squeeze8 = [bits](uint64_t x) -> uint32_t {
+        if (bits == 2) {
+            x = (x | (x >> 6)) & 0x000F000F000F000Full;
+            x = (x | (x >> 12)) & 0x000000FF000000FFull;
+            x = (x | (x >> 24)) & 0xFFFFull;
+        } else {
+            x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+            x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+            x = (x | (x >> 16)) & 0xFFFFFFFFull;
+        }
+        return (uint32_t)x;
+    };
+    const uint64_t hi_bits = bits == 2 ? 0xFCFCFCFCFCFCFCFCull : 0xF0F0F0F0F0F0F0F0ull;
+    auto work = [&](int t) {
+        const int64_t i0 = n * t / n_thr, i1 = n * (t + 1) / n_thr;
+        uint32_t mask = 0;
+        for (int64_t i = i0; i < i1; ++i) {
+            const int64_t L = len[i];
+            const uint8_t *s = codes + off[i];
+            uint32_t *dst = words + start[i];
+            int64_t k = 0;
+            for (; k + per <= L; k += per) {                       // full words
+                uint64_t x0, x1 = 0;
+                memcpy(&x0, s + k, 8);
+                if (bits == 2) memcpy(&x1, s + k + 8, 8);
+                if ((x0 | x1) & hi_bits) { if (bad[(size_t)t] < 0) bad[(size_t)t] = i; break; }
+                const uint32_t word = bits == 2 ? (squeeze8(x0) | (squeeze8(x1) << 16)) : squeeze8(x0);
+                if (bits == 2) {                                   // which of the four symbols occur: field-parallel
+                    const uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
+                    if ((~lo & ~hi) & 0x55555555u) mask |= 1u;
+                    if (lo & ~hi) mask |= 2u;
+                    if (~lo & hi) mask |= 4u;
+                    if (lo & hi) mask |= 8u;
+                } else {
+                    for (int c = 0; c < 8; ++c) mask |= 1u << ((word >> (4 * c)) & 15u);
+                }
+                *dst++ = word;
+            }
+            if (bad[(size_t)t] == i) continue;
+            if (k < L) {                                           // the last, partial word
+                uint32_t word = 0;
+                for (int c = 0; k + c < L; ++c) {
+                    const uint32_t v = s[k + c];
+                    if (v >= lim) { if (bad[(size_t)t] < 0) bad[(size_t)t] = i; continue; }
+                    mask |= 1u << v;
+                    word |= v << (bits * c);
+                }
+                *dst++ = word;
+            }
+        }
+        masks[(size_t)t] = mask;
+    };
+    if (n_thr == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    uint32_t mask = 0;
+    for (int t = 0; t < n_thr; ++t) {
+        if (bad[(size_t)t] >= 0) {
+            const int64_t i = bad[(size_t)t];
+            uint32_t v = 0;
+            for (int64_t k = off[i]; k < off[i + 1]; ++k) if (codes[k] >= lim) { v = codes[k]; break; }
+            return rsd_fail(RSD_EINVAL, "rsd_pack: code %u at sequence %lld does not fit %d bits", v, (long long)i, bits);
+        }
+        mask |= masks[(size_t)t];
+    }
     if (symmask_inout) *symmask_inout |= mask;
     return RSD_OK;
 }

@@ -880,6 +880,7 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
     const int64_t *sA = (const int64_t *)bufA.start.p, *sB = (const int64_t *)bufB.start.p;
     const int32_t *lA = (const int32_t *)bufA.len.p, *lB = (const int32_t *)bufB.len.p;
     if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+    bool rows_copied = false;
     for (size_t k = 0; k + 1 < chunk_start.size(); ++k) {
         const int64_t p0 = chunk_start[k], np = chunk_start[k + 1] - p0;
         SeqView A{dA, sA + p0, lA + p0}, B{dB, sB + p0, lB + p0};
@@ -910,17 +911,31 @@ int rsd_ctx::script_pipeline(const int32_t *a_len, const int32_t *b_len, int64_t
         if (op || oi || oj || ok) { k_finalize<<<(unsigned)np, 256, 0, st>>>(fa, np); launches += 1; }
         launches += 2;
         RSD_CUDA(cudaGetLastError());
+        // the chunk's script rows go back on the copy stream while the next chunk computes
+        if (chunk_start.size() > 2 && (op || oi || oj)) {
+            const int ev = (int)(k % RSD_MAX_CHUNKS);
+            RSD_CUDA(cudaEventRecord(ev_done[ev], st));
+            RSD_CUDA(cudaStreamWaitEvent(copy_stream, ev_done[ev], 0));
+            const size_t r0 = (size_t)p0 * max_ops, rn = (size_t)np * max_ops;
+            if (op) RSD_CUDA(cudaMemcpyAsync(op + r0, (uint8_t *)s_op.p + r0, rn, cudaMemcpyDeviceToHost, copy_stream));
+            if (oi) RSD_CUDA(cudaMemcpyAsync(oi + r0, (int32_t *)s_oi.p + r0, sizeof(int32_t) * rn, cudaMemcpyDeviceToHost, copy_stream));
+            if (oj) RSD_CUDA(cudaMemcpyAsync(oj + r0, (int32_t *)s_oj.p + r0, sizeof(int32_t) * rn, cudaMemcpyDeviceToHost, copy_stream));
+            rows_copied = true;
+        }
     }
     if (timing) { RSD_CUDA(cudaEventRecord(ev1, st)); timed = true; }
     const double t_enq = now();
     if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[rsd trace] script: host prep %.3f ms, alloc+enqueue %.3f ms, kernels done after %.3f ms, %zu chunk(s)\n",
                                                    t_plan - t_in, t_enq - t_plan, now() - t_in, chunk_start.size() - 1); }
-    if (op) RSD_CUDA(cudaMemcpyAsync(op, s_op.p, (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
-    if (oi) RSD_CUDA(cudaMemcpyAsync(oi, s_oi.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
-    if (oj) RSD_CUDA(cudaMemcpyAsync(oj, s_oj.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+    if (!rows_copied) {
+        if (op) RSD_CUDA(cudaMemcpyAsync(op, s_op.p, (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+        if (oi) RSD_CUDA(cudaMemcpyAsync(oi, s_oi.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+        if (oj) RSD_CUDA(cudaMemcpyAsync(oj, s_oj.p, sizeof(int32_t) * (size_t)n_pairs * max_ops, cudaMemcpyDeviceToHost, st));
+    }
     if (n_ops) RSD_CUDA(cudaMemcpyAsync(n_ops, s_nops.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     if (dist) RSD_CUDA(cudaMemcpyAsync(dist, out_f64.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     if (ok) RSD_CUDA(cudaMemcpyAsync(ok, s_ok.p, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (rows_copied) RSD_CUDA(cudaStreamSynchronize(copy_stream));
     RSD_CUDA(cudaStreamSynchronize(st));
     if (trace) fprintf(stderr, "[rsd trace] script: results on the host after %.3f ms\n", now() - t_in);
     return RSD_OK;

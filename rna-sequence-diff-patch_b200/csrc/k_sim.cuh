@@ -11,7 +11,8 @@
 //   k_sim_query   one warp: representations of the query (symbol mask, 4-vector, TF matrix, centred TF
 //                 matrix and their norms) -> SimQuery in global memory
 //   k_sim_small   one thread per record: set_* and multi_* measures (a mask and four sequential sums)
-//   k_sim_tf      one warp per record: TF matrix in shared memory, the vector measures
+//   k_sim_tf_thread  one thread per record made of A, G, C, U only: 16 bigram counts, the 225-term sums unrolled
+//   k_sim_tf      one warp per record (records with ambiguity codes): TF matrix in shared memory, the vector measures
 #pragma once
 #include "../../include/rsd.h"
 #include "rsd_common.cuh"
@@ -142,9 +143,11 @@ k_sim_small(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ d
 __global__ void __launch_bounds__(128)
 k_sim_tf(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_start, const int32_t *__restrict__ db_len,
          int64_t n_rec, int db_bits, const int64_t *__restrict__ perm, int64_t global_base,
-         const SimQuery *__restrict__ Q, int method, double *__restrict__ scores) {
+         const SimQuery *__restrict__ Q, int method, double *__restrict__ scores,
+         const int *__restrict__ worklist, const int *__restrict__ worklist_n) {
     __shared__ double s_a[RSD_TF];
     __shared__ double s_v[4][RSD_TF];
+    if (worklist) n_rec = *worklist_n;               // only the records the per-thread kernel deferred
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const double *qa = method == RSD_SIM_PEARSON ? Q->tfc : Q->tf;
     for (int e = threadIdx.x; e < RSD_TF; e += blockDim.x) s_a[e] = qa[e];
@@ -152,7 +155,8 @@ k_sim_tf(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_s
     const double a_sq = method == RSD_SIM_PEARSON ? Q->tfc_sq : Q->tf_sq;
     double *v = s_v[wib];
     const int64_t n_warps = (int64_t)gridDim.x * 4;
-    for (int64_t r = (int64_t)blockIdx.x * 4 + wib; r < n_rec; r += n_warps) {
+    for (int64_t rr = (int64_t)blockIdx.x * 4 + wib; rr < n_rec; rr += n_warps) {
+        const int64_t r = worklist ? (int64_t)worklist[rr] : rr;
         const int len = db_len[r];
         const int64_t st = db_start[r];
         tf_build(v, len, [&](int i) { return (int)pk_get(db_words, st, i, db_bits); });
@@ -177,6 +181,89 @@ k_sim_tf(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_s
         if (lane == 0) scores[perm[r] - global_base] = out;
         __syncwarp();
     }
+}
+
+// numpy's pairwise sum of f(0..224) evaluated by ONE thread (fully unrolled, so f sees compile-time indices)
+template <typename F>
+__device__ __forceinline__ double np_sum225_thread(F f) {
+    double blk[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = f(112 * h + j);
+#pragma unroll
+        for (int g = 1; g < 14; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(112 * h + 8 * g + j));
+        blk[h] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    }
+    blk[1] = __dadd_rn(blk[1], f(224));
+    return __dadd_rn(blk[0], blk[1]);
+}
+
+// One THREAD per stored record, for records made of A, G, C, U only (the bulk of a real database): their TF matrix
+// is 16 bigram counts in the top-left 4 x 4 corner, every other entry is exactly 0, so the matrix never has to be
+// materialised — the 225-term sums are unrolled with the 16 counts in registers.  Records that contain an
+// ambiguity code (or are too long for 16-bit counters) are appended to a worklist for k_sim_tf.
+__global__ void __launch_bounds__(128)
+k_sim_tf_thread(const uint32_t *__restrict__ db_words, const int64_t *__restrict__ db_start, const int32_t *__restrict__ db_len,
+                int64_t n_rec, int db_bits, const int64_t *__restrict__ perm, int64_t global_base,
+                const SimQuery *__restrict__ Q, int method, double *__restrict__ scores,
+                int *__restrict__ worklist, int *__restrict__ worklist_n) {
+    __shared__ double s_a[RSD_TF];
+    __shared__ uint16_t s_cnt[16][128];
+    const double *qa = method == RSD_SIM_PEARSON ? Q->tfc : Q->tf;
+    for (int e = threadIdx.x; e < RSD_TF; e += blockDim.x) s_a[e] = qa[e];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const int tid = threadIdx.x;
+    const int len = db_len[r];
+    const int64_t st = db_start[r];
+    bool plain = len <= 60000;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s_cnt[e][tid] = 0;
+    if (plain && len > 0) {
+        uint32_t prev = pk_get(db_words, st, 0, db_bits);
+        plain = prev < 4u;
+        for (int i = 1; i < len && plain; ++i) {
+            const uint32_t cur = pk_get(db_words, st, i, db_bits);
+            if (cur >= 4u) { plain = false; break; }
+            s_cnt[prev * 4 + cur][tid] += 1;                                   // IR:156
+            prev = cur;
+        }
+    }
+    if (!plain) { worklist[atomicAdd(worklist_n, 1)] = (int)r; return; }
+    double b[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) b[e] = (double)s_cnt[e][tid];
+    auto bv = [&](int e) -> double {                                           // entry e of the record's TF matrix
+        const int row = e / 15, col = e % 15;
+        return (row < 4 && col < 4) ? b[row * 4 + col] : 0.0;
+    };
+    const double a_sq = method == RSD_SIM_PEARSON ? Q->tfc_sq : Q->tf_sq;
+    double out;
+    if (method == RSD_SIM_PEARSON) {
+        // np.average of the count matrix: the counts are small integers, so their sum is exact whatever the order
+        const double avg = __ddiv_rn((double)(len > 0 ? len - 1 : 0), 225.0);
+        const double num = np_sum225_thread([&](int e) { return __dmul_rn(s_a[e], __dadd_rn(bv(e), -avg)); });
+        const double b_sq = np_sum225_thread([&](int e) { const double x = __dadd_rn(bv(e), -avg); return __dmul_rn(x, x); });
+        out = __ddiv_rn(num, __dsqrt_rn(__dmul_rn(a_sq, b_sq)));
+    } else if (method == RSD_SIM_EUCLIDEAN) {
+        const double d = np_sum225_thread([&](int e) { const double x = __dadd_rn(s_a[e], -bv(e)); return __dmul_rn(x, x); });
+        out = __ddiv_rn(1.0, __dadd_rn(1.0, __dsqrt_rn(d)));
+    } else if (method == RSD_SIM_MANHATTAN) {
+        const double d = np_sum225_thread([&](int e) { return fabs(__dadd_rn(s_a[e], -bv(e))); });
+        out = __ddiv_rn(1.0, __dadd_rn(1.0, __dsqrt_rn(d)));
+    } else {
+        const double num = np_sum225_thread([&](int e) { return __dmul_rn(s_a[e], bv(e)); });
+        const double b_sq = np_sum225_thread([&](int e) { return __dmul_rn(bv(e), bv(e)); });
+        if (method == RSD_SIM_COSINE) out = __ddiv_rn(num, __dsqrt_rn(__dmul_rn(a_sq, b_sq)));
+        else if (method == RSD_SIM_TANIMOTO) out = __ddiv_rn(num, __dadd_rn(__dadd_rn(a_sq, b_sq), -num));
+        else out = __ddiv_rn(__dmul_rn(2.0, num), __dadd_rn(a_sq, b_sq));
+    }
+    scores[perm[r] - global_base] = out;
 }
 
 // Candidates of one score range for the top-k fold (same key as the edit-distance search: score desc,

@@ -1070,7 +1070,7 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
 
 extern "C" int rsd_db_free(rsd_ctx *c) {
     if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
-    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_perm.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); c->sim_scores.release(); c->sim_aux.release(); }
+    if (c->inited && c->pid == getpid()) { cudaSetDevice(c->device); c->db.release(); c->db_perm.release(); c->db_topi.release(); c->db_tops.release(); c->db_aux.release(); c->db_dist.release(); c->sim_scores.release(); c->sim_aux.release(); c->sim_work.release(); }
     c->db_loaded = false; c->db_n = 0;
     return RSD_OK;
 }
@@ -1256,9 +1256,16 @@ extern "C" int rsd_db_similarity(rsd_ctx *c, const uint8_t *q_codes, int32_t q_l
             k_sim_small<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dbw, dbs, dbl, n, c->db_bits, (const int64_t *)c->db_perm.p, c->db_base,
                                                                      (const SimQuery *)c->sim_q.p, method, scores);
         } else {
+            // plain A/G/C/U records: one thread each; the rest (ambiguity codes) go through a worklist to the warp kernel
+            RSD_OK_OR_RETURN(c->sim_work.ensure(sizeof(int) * (size_t)(n + 16)));
+            int *wl_n = (int *)c->sim_work.p, *wl = wl_n + 4;
+            RSD_CUDA(cudaMemsetAsync(wl_n, 0, sizeof(int), st));
+            k_sim_tf_thread<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dbw, dbs, dbl, n, c->db_bits, (const int64_t *)c->db_perm.p, c->db_base,
+                                                                         (const SimQuery *)c->sim_q.p, method, scores, wl, wl_n);
             const unsigned grid = (unsigned)std::min<int64_t>((n + 3) / 4, (int64_t)c->sm_count * 16);
             k_sim_tf<<<grid, 128, 0, st>>>(dbw, dbs, dbl, n, c->db_bits, (const int64_t *)c->db_perm.p, c->db_base,
-                                           (const SimQuery *)c->sim_q.p, method, scores);
+                                           (const SimQuery *)c->sim_q.p, method, scores, wl, wl_n);
+            c->launches += 1;
         }
         c->launches += 1;
     }

@@ -105,7 +105,7 @@ struct rsd_ctx {
     uint32_t db_symmask = 0;
     bool db_loaded = false;
     DevBuf db_dist, db_topi, db_tops, db_aux, db_perm;
-    DevBuf sim_q, sim_scores, sim_aux, sim_codes;
+    DevBuf sim_q, sim_scores, sim_aux, sim_codes, sim_work;
 
     int ensure_device();
     int classify(uint32_t symmask, int64_t max_m, int64_t max_n, int bits, int force_mode, ModeInfo &mi) const;
@@ -132,7 +132,7 @@ struct rsd_ctx {
         for (PlanSlot &s : slots) s.release();
         DevBuf *all[] = {&out_f64, &mat_vals, &mat_mask, &mat_ab,
                          &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
-                         &db_dist, &db_topi, &db_tops, &db_aux, &db_perm, &sim_q, &sim_scores, &sim_aux, &sim_codes};
+                         &db_dist, &db_topi, &db_tops, &db_aux, &db_perm, &sim_q, &sim_scores, &sim_aux, &sim_codes, &sim_work};
         for (DevBuf *b : all) b->release();
     }
 };

@@ -20,6 +20,7 @@ import __graft_entry__ as G  # noqa: E402
 G.build()
 import rna_sequence_diff_patch_b200 as R  # noqa: E402
 from oracle import oracle as O  # noqa: E402
+from oracle import ir_oracle as IO  # noqa: E402
 
 DROPIN = os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin")
 DEFAULT = __import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()
@@ -85,7 +86,7 @@ def main():
         alpha = [SYM[:4], SYM[:4], SYM[:4] + "N", SYM, SYM[:2], "ACGUYR"][int(rng.integers(0, 6))]
         ckind = ["default", "user", "dyadic", "int", "decimal"][int(rng.integers(0, 5))]
         lkind = ["tiny", "short", "c2", "kb", "skew", "wide"][int(rng.integers(0, 6))]
-        what = ["dist", "dist", "script", "search", "long"][int(rng.integers(0, 5))]
+        what = ["dist", "dist", "script", "search", "long", "sim"][int(rng.integers(0, 6))]
         costs = random_costs(rng, ckind)
         eng.set_costs(costs)
         force = int(rng.choice([0, 0, 0, 2, 3]))
@@ -122,6 +123,30 @@ def main():
                         and np.array_equal(res["oj"][p, :k], oj[p, :k])
                 cells += float((np.diff(oa).astype(np.float64) * np.diff(ob)).sum())
                 desc = f"script n={n} mode={eng.last_mode}"
+            elif what == "sim":
+                n = int(rng.choice([1, 40, 400]))
+                lens = rng.integers(0, int(rng.choice([8, 40, 300])), size=n)
+                cd, od = make(rng, lens, alpha)
+                docs = [O.decode(cd[od[k]:od[k + 1]]) for k in range(n)]
+                q = O.decode(make(rng, np.array([int(rng.integers(0, 40))]), alpha)[0])
+                bits = 2 if (set(alpha) <= set("AGCU") and rng.random() < 0.5) else 4
+                eng.db_load(R.pack((cd, od), bits=bits))
+                ok = True
+                try:
+                    for method in rng.choice(IO.METHODS, size=3, replace=False):
+                        got, _, _ = eng.db_similarity(R.encode(q), str(method))
+                        qa = IO.represent(q, str(method))
+                        want = np.zeros(n)
+                        for k2, d2 in enumerate(docs):
+                            try:
+                                want[k2] = IO.score(str(method), qa, IO.represent(d2, str(method)))
+                            except ZeroDivisionError:          # set measures of two empty sequences: the reference raises, the device returns NaN
+                                want[k2] = np.nan
+                        ok = ok and bool(np.array_equal(np.isnan(got), np.isnan(want))
+                                         and np.array_equal(got[~np.isnan(got)].view(np.uint64), want[~np.isnan(want)].view(np.uint64)))
+                finally:
+                    eng.db_free()
+                desc = f"sim n={n} bits={bits} qlen={len(q)} mode=0"
             elif what == "long":
                 m, n2 = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
                 al = np.array([SYM.index(ch) for ch in alpha], np.uint8)

@@ -77,3 +77,9 @@ class ShardedSearch:
     def search(self, Q: PackedSeqs, k: int):
         idx, sc = self.engine.db_search_topk(Q, k)
         return gather_merge(idx, sc, self.group, self.device)
+
+    def similarity(self, query_codes: np.ndarray, method: str, k: int):
+        """Top-k of one of Engine.SIM_METHODS over the sharded database: local top-k, the same all_gather + merge
+        (a shard with fewer than k rankable records pads with index -1, which the merge skips)."""
+        _, idx, sc = self.engine.db_similarity(query_codes, method, k=k, want_scores=False)
+        return gather_merge(idx[None, :], sc[None, :], self.group, self.device)

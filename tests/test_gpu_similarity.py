@@ -132,3 +132,29 @@ def test_dropin_search_collection_serves_every_measure(R, gir):
         assert len(got["wf"]) == len(gir["docs"]) and len(got["mean"]) == len(set(gir["docs"]))
     finally:
         os.chdir(cwd)
+
+
+def test_sharded_similarity_topk_equals_single_shard(R, eng):
+    """The similarity top-k over contiguous shards (local top-k + merge) == the top-k over the whole database."""
+    from rna_sequence_diff_patch_b200.dist_search import shard_bounds, slice_packed
+    from rna_sequence_diff_patch_b200.engine import topk_merge
+    rng = np.random.default_rng(34)
+    docs = ["".join(rng.choice(list("AGCUN"), size=int(L))) for L in rng.integers(2, 40, size=5000)]
+    P = R.pack(docs, bits=4)
+    q = R.encode(docs[7])
+    for method in ("cosine", "set_dice_similarity", "multi_jaccard_similarity"):
+        eng.db_load(P)
+        try:
+            _, wi, ws = eng.db_similarity(q, method, k=12, want_scores=False)
+        finally:
+            eng.db_free()
+        parts_i, parts_s = [], []
+        for lo, hi in shard_bounds(P.len, 3):
+            eng.db_load(slice_packed(P, lo, hi), global_index_base=lo)
+            try:
+                _, i, s = eng.db_similarity(q, method, k=12, want_scores=False)
+            finally:
+                eng.db_free()
+            parts_i.append(i[None, :]); parts_s.append(s[None, :])
+        mi, ms = topk_merge(np.stack(parts_i), np.stack(parts_s))
+        assert np.array_equal(mi[0], wi) and np.array_equal(ms[0], ws), method

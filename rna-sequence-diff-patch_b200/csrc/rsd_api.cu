@@ -1146,7 +1146,16 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
         // a short first chunk (its queries spread over blockIdx.y) seeds tau; the rest goes in equal chunks <= cap
         const int64_t rest = std::max<int64_t>(db_n - CH0, 0);
         const int64_t n_main = (rest + cap - 1) / std::max<int64_t>(cap, 1);
-        const int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
+        int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
+        if (fast && !getenv("RSD_SEARCH_NOWAVE")) {
+            // the CTAs of a chunk do equal work (the database is sorted by length), so they finish wave by wave: a chunk
+            // that is a whole number of waves (resident CTAs x 256 records) leaves no partly filled last wave
+            int per_sm = 0;
+            const size_t smem_q = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
+            RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_twin16, 128, smem_q));
+            const int64_t wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
+            if (rest > wave && cap >= wave) main_sz = cap / wave * wave;
+        }
         for (int64_t r0 = 0; r0 < db_n;) {
             const bool seed = r0 == 0 && db_n > CH0;
             const int64_t nr = std::min<int64_t>(seed ? CH0 : main_sz, db_n - r0);

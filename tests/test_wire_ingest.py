@@ -57,3 +57,44 @@ def test_es_json_roundtrip_and_packed_conversions(pkg, golden, tmp_path):
         assert code == 0 and O.decode(back) == c["a"]
         n += 1
     assert n > 250
+
+
+def test_pack_word_boundaries_threads_and_errors():
+    """rsd_pack (host): every length around the 16- / 8-symbol word boundaries, both packings, the threaded path
+    (>= 4 M symbols) and the error for a code that does not fit — in a full word and in a tail."""
+    import numpy as np
+    import rna_sequence_diff_patch_b200 as R
+    from rna_sequence_diff_patch_b200.encoding import unpack
+    rng = np.random.default_rng(5)
+    for bits, alpha in ((2, 4), (4, 15)):
+        lens = np.array(list(range(0, 70)) * 3, np.int64)
+        off = np.zeros(lens.shape[0] + 1, np.int64); np.cumsum(lens, out=off[1:])
+        codes = rng.integers(0, alpha, size=int(off[-1]), dtype=np.uint8)
+        P = R.pack((codes, off), bits=bits)
+        c2, o2 = unpack(P)
+        assert np.array_equal(c2, codes) and np.array_equal(o2, off)
+        per = 32 // bits
+        assert np.array_equal(P.start, np.concatenate([[0], np.cumsum((lens + per - 1) // per)[:-1]]))
+        want_mask = 0
+        for v in np.unique(codes):
+            want_mask |= 1 << int(v)
+        assert P.symmask == want_mask
+        for pos in (3, int(off[40]) + 35, int(off[-1]) - 1):            # first word, a tail, the very last symbol
+            bad = codes.copy(); bad[pos] = 1 << bits
+            try:
+                R.pack((bad, off), bits=bits)
+                assert False, "code out of range accepted"
+            except R.RsdError as e:
+                assert "does not fit" in str(e)
+    # threaded path
+    n = 60000
+    lens = rng.integers(40, 120, size=n)
+    off = np.zeros(n + 1, np.int64); np.cumsum(lens, out=off[1:])
+    assert off[-1] >= (1 << 22)
+    codes = rng.integers(0, 4, size=int(off[-1]), dtype=np.uint8)
+    P = R.pack((codes, off))
+    assert P.bits == 2 and P.symmask == 0xF
+    sub = R.PackedSeqs(P.words, P.start[:2000], P.len[:2000], P.bits, P.symmask)
+    assert np.array_equal(unpack(sub)[0], codes[:off[2000]])
+    tail = R.PackedSeqs(P.words, P.start[-500:], P.len[-500:], P.bits, P.symmask)
+    assert np.array_equal(unpack(tail)[0], codes[off[n - 500]:])

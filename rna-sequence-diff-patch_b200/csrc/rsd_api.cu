@@ -1049,13 +1049,27 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
     for (int64_t i = 0; i < n_records; ++i) perm[(size_t)cnt[(size_t)len[i]]++] = i;
     std::vector<uint32_t> s_words((size_t)n_words + 8, 0u);
     int64_t w = 0;
-    for (int64_t r = 0; r < n_records; ++r) {
+    for (int64_t r = 0; r < n_records; ++r) {                       // offsets in stored order (serial, cheap)
         const int64_t i = perm[(size_t)r];
         const int64_t nw = ((int64_t)len[i] + per - 1) / per;
         if (start[i] < 0 || start[i] + nw > n_words) return rsd_fail(RSD_EINVAL, "rsd_db_load: record %lld lies outside the word buffer", (long long)i);
         s_start[(size_t)r] = w; s_len[(size_t)r] = len[i];
-        memcpy(s_words.data() + w, words + start[i], sizeof(uint32_t) * (size_t)nw);
         w += nw;
+    }
+    {                                                               // the gather itself, split over the host threads
+        const int n_thr = n_records >= (1 << 18) ? (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32) : 1;
+        auto work = [&](int t) {
+            for (int64_t r = n_records * t / n_thr, r1 = n_records * (t + 1) / n_thr; r < r1; ++r) {
+                const int64_t i = perm[(size_t)r];
+                memcpy(s_words.data() + s_start[(size_t)r], words + start[i], sizeof(uint32_t) * (size_t)(((int64_t)len[i] + per - 1) / per));
+            }
+        };
+        if (n_thr == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
+            for (auto &th : pool) th.join();
+        }
     }
     RSD_OK_OR_RETURN(c->upload_seqs(c->db, s_words.data(), s_start.data(), s_len.data(), n_records, std::max<int64_t>(w, 1), c->stream));
     RSD_OK_OR_RETURN(c->db_perm.ensure(sizeof(int64_t) * (size_t)std::max<int64_t>(n_records, 1)));

@@ -62,6 +62,9 @@ def c3(eng, n_pairs, reps=3):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p(); _lib.check(lib.rsd_host_alloc(C.byref(ptr), n))
         return np.frombuffer((C.c_uint8 * n).from_address(ptr.value), dtype=dtype).reshape(shape)
+    for P in (A, B):                              # page-locked inputs as well
+        for name in ("words", "start", "len"):
+            src = getattr(P, name); dst = pinned(src.shape, src.dtype); dst[...] = src; setattr(P, name, dst)
     op = pinned((n_pairs, max_ops), np.uint8); n_ops = pinned((n_pairs,), np.int32); dist = pinned((n_pairs,), np.float64)
     ok = pinned((n_pairs,), np.uint8); mode = C.c_int()
     ts, kms = [], []

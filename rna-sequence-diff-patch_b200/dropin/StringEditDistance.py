@@ -2,8 +2,10 @@
 
 Same names, argument meaning and error behaviour as /root/reference/StringEditDistance.py; the
 matrix fill runs on the GPU through librsd.so.  Like the reference (SED:6-18) the cost files are
-read from the current working directory at import; when a file is absent there, the same table
-built into the package (cost_tables.py) is used.  The reference's import-time self-test print (SED:463-471) is
+read from the current working directory at import: `costs.json` (when it is absent the identical table
+built into cost_tables.py is used, where the reference would raise FileNotFoundError), and
+`user_costs.json` — when THAT is absent user_costs is the default table itself (the same object) and the
+reference's notice is printed (SED:12-18).  The reference's import-time self-test print (SED:463-471) is
 not reproduced: call selftest()."""
 import json
 import os
@@ -21,15 +23,18 @@ from rna_sequence_diff_patch_b200.sed import Edge, Node  # noqa: E402,F401
 from rna_sequence_diff_patch_b200 import cost_tables as _tables  # noqa: E402
 
 
-def _load_cost_file(name, builtin):
-    if os.path.exists(name):
-        with open(name, "r") as f:
-            return json.load(f)
-    return builtin()
+if os.path.exists("costs.json"):
+    with open("costs.json", "r") as f:
+        default_costs = json.load(f)
+else:
+    default_costs = _tables.default_costs()
 
-
-default_costs = _load_cost_file("costs.json", _tables.default_costs)
-user_costs = _load_cost_file("user_costs.json", _tables.user_costs)
+try:
+    with open("user_costs.json", "r") as f:
+        user_costs = json.load(f)
+except (OSError, IOError):
+    user_costs = default_costs                       # SED:16: an alias of the default table, not a copy
+    print('Could not find user costs file')
 
 
 def reload_user_costs():

@@ -157,9 +157,11 @@ class Engine:
                                     db.n, db.words.shape[0], db.bits, db.symmask, global_index_base))
         self._db_n = db.n
         self._db_bits = db.bits
+        self._db_gen = getattr(self, "_db_gen", 0) + 1      # lets callers that keep a database resident notice a reload
 
     def db_free(self):
         check(self._lib.rsd_db_free(self._ctx))
+        self._db_gen = getattr(self, "_db_gen", 0) + 1
 
     def db_search_topk(self, Q: PackedSeqs, k: int, want_scores: bool = False, force_mode: int = 0):
         """-> (top_idx int64[q,k], top_score f64[q,k][, all_scores f64[q, n_db]])."""

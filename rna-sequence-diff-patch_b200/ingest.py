@@ -1,14 +1,15 @@
 """ingest.py — sequence files -> packed database.
 
 Mirrors the normalisation of the reference's importers (fa_import.py:61-62, import_xml.py:12-13:
-T -> U, X -> N) and their record shape ({id: sequence}); replaces the MongoDB collection scan of
-IRMethods.search_collection (IR:469) by a packed, device-resident database.  Unlike fa_import.py
-(which imports only the first 500 records and drops the file's last one, fa_import.py:22,43-55) every
-record is kept."""
+T -> U, X -> N); replaces the MongoDB collection scan of IRMethods.search_collection (IR:469) by a packed,
+device-resident database.  Like fa_import.py:49 every record becomes a document of the collection whatever its
+title (records are a list of (title, sequence): repeated titles do not overwrite each other) and the title is the
+whole header line (fa_import.py:56); unlike it (first 500 records only, the file's last record dropped,
+fa_import.py:22,43-55) every record of the file is kept.  normalise() also strips white space and upper-cases,
+which the reference's importers leave to the GUI's input check (gui.py:62-69)."""
 from __future__ import annotations
 
 import xml.etree.ElementTree as ET
-from collections import OrderedDict
 
 from .encoding import PackedSeqs, pack
 
@@ -17,31 +18,28 @@ def normalise(seq: str) -> str:
     return seq.strip().upper().replace("T", "U").replace("X", "N")
 
 
-def read_seqxml(path: str) -> "OrderedDict[str, str]":
+def read_seqxml(path: str) -> "list[tuple[str, str]]":
     """import_xml.py:4-17 — <entry id=...><RNAseq>...</RNAseq></entry>."""
-    out: "OrderedDict[str, str]" = OrderedDict()
-    for entry in ET.parse(path).getroot().findall("entry"):
-        out[entry.get("id")] = normalise(entry.find("RNAseq").text)
-    return out
+    return [(entry.get("id"), normalise(entry.find("RNAseq").text)) for entry in ET.parse(path).getroot().findall("entry")]
 
 
-def read_fasta(path: str) -> "OrderedDict[str, str]":
-    """fa_import.py:39-62 — '>' header line, sequence possibly over several lines; all records."""
-    out: "OrderedDict[str, str]" = OrderedDict()
+def read_fasta(path: str) -> "list[tuple[str, str]]":
+    """fa_import.py:39-62 — '>' header line (the whole line is the title), sequence possibly over several lines."""
+    out: "list[tuple[str, str]]" = []
     name, parts = None, []
     with open(path) as f:
         for line in f:
-            line = line.strip()
-            if not line:
+            line = line.rstrip("\r\n")
+            if not line.strip():
                 continue
             if line.startswith(">"):
                 if name is not None:
-                    out[name] = normalise("".join(parts))
-                name, parts = line[1:].split()[0] if len(line) > 1 else str(len(out)), []
+                    out.append((name, normalise("".join(parts))))
+                name, parts = line[1:], []
             else:
-                parts.append(line)
+                parts.append(line.strip())
     if name is not None:
-        out[name] = normalise("".join(parts))
+        out.append((name, normalise("".join(parts))))
     return out
 
 
@@ -49,9 +47,10 @@ class SequenceDB:
     """ids + packed sequences; `collection.find({})`-compatible so it can stand in for the Mongo
     collection the reference's callers pass around (IR:469)."""
 
-    def __init__(self, records: "OrderedDict[str, str] | dict"):
-        self.ids = list(records.keys())
-        self.sequences = [records[k] for k in self.ids]
+    def __init__(self, records: "list[tuple[str, str]] | dict"):
+        items = list(records.items()) if isinstance(records, dict) else list(records)
+        self.ids = [k for k, _ in items]
+        self.sequences = [v for _, v in items]
         self.packed: PackedSeqs = pack(self.sequences, bits=4)
 
     @classmethod

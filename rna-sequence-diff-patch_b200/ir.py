@@ -21,6 +21,51 @@ def wf_score(seq1: str, seq2: str, costs: dict) -> float:
     return 1 / (1 + sed.distance(seq1, seq2, costs))
 
 
+def _validate_collection(query: str, sequences, costs: dict):
+    """The reference raises KeyError for the first (document, row symbol, column symbol) whose update cost is not in
+    the table (SED:87 through IR:437).  One pass over the distinct symbols of the whole collection decides whether
+    any document can fail; only then is the per-document check (which finds the reference's first error) run."""
+    upd = costs["update"]
+    doc_syms = set().union(*map(set, sequences)) if len(sequences) < 64 else set("".join(sequences))
+    clean = True
+    for c1 in set(query):
+        row = upd.get(c1)
+        for c2 in doc_syms:
+            if c2.lower() != c1.lower() and (row is None or c2 not in row):
+                clean = False
+    if not clean:
+        for s in sequences:
+            sed._validate_and_encode(query, s, costs)
+
+
+class _Resident:
+    """The collection last loaded by score_collection / similarity_collection: a session that searches the same
+    collection again (gui.py:532-600: every search re-reads collection.find({})) pays rsd_db_load once."""
+    engine = None
+    sequences = None
+    gen = -1
+
+    @classmethod
+    def load(cls, eng, sequences, upper: bool):
+        if (cls.engine is eng and cls.gen == getattr(eng, "_db_gen", 0) and cls.sequences is not None
+                and cls.sequences[0] == upper and cls.sequences[1] == sequences):
+            return
+        cls.engine, cls.sequences = None, None
+        eng.db_load(pack([s.upper() for s in sequences] if upper else sequences, bits=4))
+        cls.engine, cls.sequences, cls.gen = eng, (upper, sequences), eng._db_gen
+
+    @classmethod
+    def drop(cls):
+        if cls.engine is not None and cls.gen == getattr(cls.engine, "_db_gen", 0):
+            cls.engine.db_free()
+        cls.engine, cls.sequences = None, None
+
+
+def release_collection():
+    """Free the device copy of the collection kept by the last search (optional; the next search reloads)."""
+    _Resident.drop()
+
+
 def score_collection(query: str, sequences, costs: dict, engine=None):
     """[(sequence, wf_score(query, sequence))] in collection order — what
     search_collection(query, _, collection, wf_score) returns (IR:469-477), one GPU pass."""
@@ -29,14 +74,9 @@ def score_collection(query: str, sequences, costs: dict, engine=None):
         return []
     eng = engine or get_engine()
     eng.set_costs(costs)
-    for s in sequences:                       # the reference's per-document KeyError (SED:87)
-        sed._validate_and_encode(query, s, costs)
-    up = [s.upper() for s in sequences]
-    eng.db_load(pack(up, bits=4))
-    try:
-        _, _, scores = eng.db_search_topk(pack([query.upper()], bits=4), k=1, want_scores=True)
-    finally:
-        eng.db_free()
+    _validate_collection(query, sequences, costs)
+    _Resident.load(eng, sequences, upper=True)
+    _, _, scores = eng.db_search_topk(pack([query.upper()], bits=4), k=1, want_scores=True)
     return [(s, float(v)) for s, v in zip(sequences, scores[0])]
 
 
@@ -58,11 +98,8 @@ def similarity_collection(query: str, sequences, method: str, engine=None):
     from .encoding import encode
     eng = engine or get_engine()
     qc = encode(query)
-    eng.db_load(pack(sequences, bits=4))
-    try:
-        scores, _, _ = eng.db_similarity(qc, method)
-    finally:
-        eng.db_free()
+    _Resident.load(eng, sequences, upper=False)
+    scores, _, _ = eng.db_similarity(qc, method)
     return [(s, float(v)) for s, v in zip(sequences, scores)]
 
 

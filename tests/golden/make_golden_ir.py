@@ -78,6 +78,40 @@ def main():
     for s in docs[len(xml):len(xml) + 14] + queries:                 # representation vectors themselves
         out["tf"][s] = [hx(v) for v in IR.convert_to_tf_vector(s).reshape(-1)]
         out["multiset"][s] = [hx(v) for v in IR.convert_to_multi_set(s)]
+    # ---- idf / tf-idf vectors (IR:189-223) and the search over them (IR:458-465): a collection whose documents
+    # carry the 'idf' vector update_idfs() would have stored (fa_import.py:30-36, commented out in the reference)
+    small = docs[len(xml) + 6:len(xml) + 14] + docs[-6:] + xml[:6]
+    class CollIdf:
+        def __init__(self, seqs):
+            self.docs = [{'sequence': s} for s in seqs]
+            for d in self.docs:
+                d['tf'] = pickle.dumps(IR.convert_to_tf_vector(d['sequence']))
+            for d in self.docs:
+                d['idf'] = pickle.dumps(IR.convert_to_idf_vector(d['sequence'], self))
+        def find(self, _):
+            return iter(self.docs)
+        def count_documents(self, _):
+            return len(self.docs)
+    cidf = CollIdf(small)
+    out["idf_docs"] = small
+    out["idf"] = {d['sequence']: [hx(v) for v in pickle.loads(d['idf']).reshape(-1)] for d in cidf.docs}
+    out["idf_pairlist"] = {}
+    for a, b in [(small[0], small[1]), (small[3], small[9]), ('AN', 'ACGU')]:       # gui.py:480-484 shape
+        out["idf_pairlist"][a + "|" + b] = {
+            "idf_a": [hx(v) for v in IR.convert_to_idf_vector(a, list_of_docs=[a, b]).reshape(-1)],
+            "tfidf_a": [hx(v) for v in IR.create_tf_idf_vector(a, list_of_docs=[a, b]).reshape(-1)],
+            "tfidf_b": [hx(v) for v in IR.create_tf_idf_vector(b, list_of_docs=[a, b]).reshape(-1)]}
+    out["idf_scores"] = {}
+    for q in [small[2], queries[1], 'AN']:
+        out["idf_scores"][q] = {}
+        for vt in ('idf', 'tf-idf'):
+            out["idf_scores"][q][vt] = {}
+            for name in METHODS[6:]:
+                res = IR.search_collection(q, vt, cidf, getattr(IR, name))
+                out["idf_scores"][q][vt][name] = [hx(v) for _, v in res]
+    out["compare_pair"] = [[p, s, hx(IR.compare_pair_to_seq(p, s, is_document=False))]
+                           for p in ('AA', 'AN', 'NN', 'YR', 'GU', 'BD') for s in small[:8]]
+    out["possibilities"] = {c: [IR.possibilities(c)[0], [hx(v) for v in IR.possibilities(c)[1]]] for c in NUC}
     with open(OUT, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(docs), "docs,", len(queries), "queries")

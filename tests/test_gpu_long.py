@@ -1,7 +1,12 @@
 """GPU parity: the long-pair path (panel wavefront + traceback) vs the oracle and via properties."""
+import hashlib
+import json
+import os
+
 import numpy as np
 import pytest
 
+from _synth import c4_pair, mutate_codes
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -19,21 +24,6 @@ def R():
 @pytest.fixture(scope="module")
 def eng(R):
     return R.Engine(0)
-
-
-def mutate_codes(rng, a, alpha=4, p_sub=0.05, p_ins=0.025, p_del=0.025):
-    r = rng.random(a.shape[0])
-    keep = r >= p_del
-    out = []
-    sub = rng.integers(0, alpha, size=a.shape[0], dtype=np.uint8)
-    ins = rng.integers(0, alpha, size=a.shape[0], dtype=np.uint8)
-    for k in range(a.shape[0]):
-        if not keep[k]:
-            continue
-        out.append(sub[k] if r[k] < p_del + p_sub else a[k])
-        if r[k] > 1 - p_ins:
-            out.append(ins[k])
-    return np.array(out, dtype=np.uint8)
 
 
 def apply_script(op, oj, b):
@@ -78,13 +68,87 @@ def test_empty_sides(R, eng, golden):
     assert r["dist"] == 6.0 and r["op"].tolist() == [0, 0, 0] and r["oj"].tolist() == [1, 2, 3]
 
 
+def _sha(arr, dt):
+    return hashlib.sha256(np.ascontiguousarray(arr, dtype=dt).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def c4_digest():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_digest.json")) as f:
+        return json.load(f)
+
+
+def _check_digest(res, rec):
+    assert res["dist"] == float.fromhex(rec["dist"])
+    assert res["op"].shape[0] == rec["n_ops"]
+    assert _sha(res["op"], np.uint8) == rec["op_sha256"], "canonical script differs from the oracle's (ops)"
+    assert _sha(res["oi"], np.int32) == rec["oi_sha256"] and _sha(res["oj"], np.int32) == rec["oj_sha256"]
+
+
+def test_c4_canonical_script_equals_oracle_digest(R, eng, golden, c4_digest):
+    """50 kb x 50 kb (BASELINE config 4), where the kernel's keys are carried modulo 2^32 and wrap: the whole
+    canonical script (= create_paths(dp)[0], SED:228-271) must equal the oracle's, recorded as SHA-256 by
+    tests/golden/make_golden_c4.py; both cost tables, plus every other kernel variant on the default one."""
+    a, b = c4_pair()
+    for name in ("default_costs", "user_costs"):
+        eng.set_costs(golden[name])
+        res = eng.long_pair(a, b)
+        assert res["mode"] == 2
+        _check_digest(res, c4_digest["c4_" + name])
+    rng = np.random.default_rng(20260044)
+    a2 = rng.integers(0, 4, size=30000, dtype=np.uint8); b2 = rng.integers(0, 4, size=50000, dtype=np.uint8)
+    _check_digest(eng.long_pair(a2, b2), c4_digest["random_30k_50k_user_costs"])
+
+
+def test_c4_other_kernel_variants_equal_oracle_digest(R, eng, golden, c4_digest, monkeypatch):
+    a, b = c4_pair()
+    eng.set_costs(golden["default_costs"])
+    for env in ({"RSD_LONG_R1": "1"}, {"RSD_LONG_WIDE": "1"}, {"RSD_LONG_C": "8"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _check_digest(eng.long_pair(a, b), c4_digest["c4_default_costs"])
+        for k in env:
+            monkeypatch.delenv(k)
+    _check_digest(eng.long_pair(a, b, force_mode=3), c4_digest["c4_default_costs"])     # fp64 kernel, same script
+
+
+def test_30k_pair_vs_oracle_in_the_wrap_regime(R, eng, golden):
+    """30 kb x 30 kb: i*del + j*ins passes 2^(31-S) (S = 16) half-way through the matrix, so the second half runs
+    on wrapped keys; compared with the oracle run here (about 6 s of CPU)."""
+    rng = np.random.default_rng(30030)
+    a = rng.integers(0, 4, size=30000, dtype=np.uint8)
+    b = mutate_codes(rng, a, p_sub=0.08, p_ins=0.04, p_del=0.04)
+    costs = golden["user_costs"]
+    eng.set_costs(costs)
+    ops, oi, oj, d = O.canonical_script(O.decode(a), O.decode(b), costs)
+    res = eng.long_pair(a, b)
+    assert res["mode"] == 2 and res["dist"] == d
+    assert np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
+
+
+@pytest.mark.parametrize("S", [19, 21])
+def test_forced_wide_steps_field_wraps_small_matrices(R, eng, golden, monkeypatch, S):
+    """RSD_LONG_S widens the steps field so the modular keys wrap after 2^(31-S) border units: at S = 21 a
+    3 k x 3 k matrix wraps six times (user costs: del 3, ins 2) — every (cost, steps) comparison still has to
+    order the candidates like the oracle."""
+    monkeypatch.setenv("RSD_LONG_S", str(S))
+    for seed, (m, n) in enumerate([(3000, 3000), (2500, 3300), (1200, 4000)]):
+        rng = np.random.default_rng(900 + seed)
+        a = rng.integers(0, 4, size=m, dtype=np.uint8)
+        b = mutate_codes(rng, a)[:n] if seed == 0 else rng.integers(0, 4, size=n, dtype=np.uint8)
+        for costs in (golden["user_costs"], golden["default_costs"]):
+            eng.set_costs(costs)
+            ops, oi, oj, d = O.canonical_script(O.decode(a), O.decode(b), costs)
+            res = eng.long_pair(a, b)
+            assert res["mode"] == 2 and res["dist"] == d
+            assert np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
+
+
 def test_c4_shape_properties(R, eng, golden):
-    """50 kb x 50 kb (BASELINE config 4): no CPU oracle at this size in a test budget; check
-    (i) the script is a valid path whose cost equals the reported distance, (ii) patching A with it
-    gives B, (iii) the distance agrees with the batched distance kernel (independent code path)."""
-    rng = np.random.default_rng(20260004)
-    a = rng.integers(0, 4, size=50000, dtype=np.uint8)
-    b = mutate_codes(rng, a)
+    """50 kb x 50 kb: size-independent properties next to the digest — (i) the script is a valid path whose cost
+    equals the reported distance, (ii) patching A with it gives B, (iii) the distance agrees with the batched
+    distance kernel (independent code path)."""
+    a, b = c4_pair()
     eng.set_costs(golden["default_costs"])
     res = eng.long_pair(a, b)
     op, oi, oj = res["op"], res["oi"], res["oj"]

@@ -24,11 +24,17 @@ def test_seqxml_and_fasta_ingest(pkg, golden, tmp_path):
     xml.write_text('<?xml version="1.0"?>\n<seqXML>\n' + "\n".join(
         f'  <entry id="{i}" >\n    <RNAseq>{s}</RNAseq>\n  </entry>' for i, s in zip(golden["xml_ids"], dna)) + "\n</seqXML>\n")
     recs = ingest.read_seqxml(str(xml))
-    assert list(recs.keys()) == golden["xml_ids"] and list(recs.values()) == golden["xml_seqs"]
+    assert [k for k, _ in recs] == golden["xml_ids"] and [v for _, v in recs] == golden["xml_seqs"]
     fa = tmp_path / "in.fa"
-    fa.write_text("".join(f">{i} some description\n{s[:10]}\n{s[10:]}\n" for i, s in zip(golden["xml_ids"], dna)) + ">last\nACGTX\n")
+    # repeated titles and titles with a common first word: every record is a document of its own (fa_import.py:49),
+    # the title is the whole header line (fa_import.py:56)
+    fa.write_text("".join(f">{i} some description\n{s[:10]}\n{s[10:]}\n" for i, s in zip(golden["xml_ids"], dna)) +
+                  ">last\nACGTX\n>dup x\nAAT\n>dup y\nCCX\n>dup x\nGG\n")
     recs = ingest.read_fasta(str(fa))
-    assert list(recs.values())[:-1] == golden["xml_seqs"] and recs["last"] == "ACGUN"
+    assert [v for _, v in recs[:-4]] == golden["xml_seqs"]
+    assert recs[-4:] == [("last", "ACGUN"), ("dup x", "AAU"), ("dup y", "CCN"), ("dup x", "GG")]
+    assert recs[0][0] == golden["xml_ids"][0] + " some description"
+    assert len(ingest.SequenceDB(recs)) == len(golden["xml_seqs"]) + 4
     db = ingest.SequenceDB.from_file(str(xml))
     assert len(db) == 25 and [d["sequence"] for d in db.find({})] == golden["xml_seqs"]
     from rna_sequence_diff_patch_b200.encoding import unpack

@@ -253,11 +253,22 @@ def main():
         return C.cast(t.data_ptr(), C.POINTER(typ))
 
     def step_e2e():
+        # packed words + lengths from pinned host memory; the batch has rsd_pack's layout, so start[] stays on the
+        # host (NULL) and is rebuilt on the device from the lengths
         mode = C.c_int()
         _lib.check(lib.rsd_distance_batch(
-            eng.ctx, cptr(hp["aw"], C.c_uint32), cptr(hp["as_"], C.c_int64), cptr(hp["al"], C.c_int32), A.words.shape[0],
-            cptr(hp["bw"], C.c_uint32), cptr(hp["bs"], C.c_int64), cptr(hp["bl"], C.c_int32), B.words.shape[0],
+            eng.ctx, cptr(hp["aw"], C.c_uint32), None, cptr(hp["al"], C.c_int32), A.words.shape[0],
+            cptr(hp["bw"], C.c_uint32), None, cptr(hp["bl"], C.c_int32), B.words.shape[0],
             args.pairs, max_m, max_n, A.bits, symmask, 0, cptr(out_host, C.c_double), C.byref(mode)))
+
+    hc = {"ca": pin(ca), "cb": pin(cb)}                    # raw symbol codes, 1 byte per symbol (what the CPU arm consumes)
+    out_codes = torch.zeros(args.pairs, dtype=torch.float64).pin_memory()
+
+    def step_codes():
+        mode = C.c_int()
+        _lib.check(lib.rsd_distance_batch_codes(
+            eng.ctx, cptr(hc["ca"], C.c_uint8), cptr(hp["al"], C.c_int32), cptr(hc["cb"], C.c_uint8), cptr(hp["bl"], C.c_int32),
+            args.pairs, max_m, max_n, A.bits, symmask, 0, cptr(out_codes, C.c_double), C.byref(mode)))
 
     def barrier():
         if world > 1:
@@ -308,15 +319,35 @@ def main():
         step_e2e()
         e2e_s += time.perf_counter() - t0
     barrier()
-    sampler.stop_flag.set(); sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = cells_all * args.steps / e2e_s * 1e-9
-    h2d = int(sum(v.numel() * v.element_size() for v in hp.values()))
+    h2d = int(sum(hp[k].numel() * hp[k].element_size() for k in ("aw", "al", "bw", "bl")))
     d2h = int(out_host.numel() * 8)
     assert np.array_equal(out_host.numpy(), check_dev), "host and device entry points disagree"
+
+    # ---- the same from raw symbol codes (ingest included: the codes are packed on the device) -------------
+    for _ in range(2):
+        step_codes()
+    barrier()
+    codes_s = 0.0
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_codes()
+        codes_s += time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([codes_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        codes_s = float(t.item())
+    sampler.stop_flag.set(); sampler.join(timeout=2)
+    assert np.array_equal(out_codes.numpy(), check_dev), "rsd_distance_batch_codes disagrees with the packed entry points"
+    e2e_codes = {"value": cells_all * args.steps / codes_s * 1e-9, "unit": "GCUPS", "ms_per_step": codes_s / args.steps * 1e3,
+                 "h2d_bytes_per_step": int(hc["ca"].numel() + hc["cb"].numel() + 8 * args.pairs), "d2h_bytes_per_step": d2h,
+                 "what": "rsd_distance_batch_codes: 1 byte per symbol from pinned host memory, packed on the device per chunk"}
 
     if rank != 0:
         if world > 1:
@@ -393,6 +424,7 @@ def main():
         "config": config, "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
+        "e2e_from_codes": e2e_codes,
         "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
         "clocks": sampler.summary(), "other_configs": extras})])
     if world > 1:

@@ -98,16 +98,28 @@ int rsd_pack(const uint8_t *codes, const int64_t *off, int64_t n, int bits,
  * (0 = let the library scan a_len / b_len; an understated bound is an error the library cannot see).
  * force_mode: 0 = classify, or one of RSD_MODE_* (tests use it to cross-check the modes; forcing
  * an INT mode on costs that are not exactly representable fails with RSD_EINVAL).
+ * a_start / b_start may be NULL: the side then has rsd_pack's canonical layout (sequence p starts at word
+ * sum_{q<p} nwords(len[q])) and its offsets are rebuilt on the device from the lengths — 8 bytes per sequence
+ * that never cross PCIe, and no layout check on the host.
  * Large batches are copied in five growing chunks on a copy stream while earlier chunks compute; that needs the
- * sequences stored in pair order (start[] non-decreasing, as rsd_pack writes them) — when the chunk
- * boundaries are not ordered the whole batch is copied first.
+ * sequences stored in pair order without overlap (checked in one pass over caller-supplied start[] / len[]) —
+ * otherwise the whole batch is copied first.
  * A context serialises its own work: do not overlap calls on one context from several streams. */
 int rsd_distance_batch(rsd_ctx *ctx,
                        const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
                        const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
                        int64_t n_pairs, int64_t max_m, int64_t max_n, int bits, uint32_t symmask, int force_mode,
                        double *out, int *mode_out);
-/* same, all pointers are device pointers, asynchronous on `stream` (a cudaStream_t) */
+/* same from RAW symbol codes (1 byte per symbol, sequences concatenated without gaps in pair order, as the
+ * reference's callers hold their strings: wagnerFisher(str1, str2), SED:133): the codes are copied chunk by chunk
+ * and packed on the device (k_pack_codes), so ingest overlaps the kernels instead of preceding them.
+ * bits: packing to use (2 needs every code < 4; a code that does not fit fails with RSD_EINVAL after the call's
+ * work); symmask: symbols present, 0 = unknown (classified as if every symbol the packing can hold occurred). */
+int rsd_distance_batch_codes(rsd_ctx *ctx, const uint8_t *a_codes, const int32_t *a_len,
+                             const uint8_t *b_codes, const int32_t *b_len, int64_t n_pairs,
+                             int64_t max_m, int64_t max_n, int bits, uint32_t symmask, int force_mode,
+                             double *out, int *mode_out);
+/* rsd_distance_batch with device pointers, asynchronous on `stream` (a cudaStream_t) */
 int rsd_distance_batch_dev(rsd_ctx *ctx,
                            const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len,
                            const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "rsd_pack_words": (i64, [i32p, i64, ci]),
     "rsd_pack": (ci, [u8p, i64p, i64, ci, u32p, i64p, i32p, u32p]),
     "rsd_distance_batch": (ci, [vp, u32p, i64p, i32p, i64, u32p, i64p, i32p, i64, i64, i64, i64, ci, u32, ci, f64p, intp]),
+    "rsd_distance_batch_codes": (ci, [vp, u8p, i32p, u8p, i32p, i64, i64, i64, ci, u32, ci, f64p, intp]),
     "rsd_distance_batch_dev": (ci, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, u32, ci, vp, intp, vp]),
     "rsd_matrix": (ci, [vp, u8p, C.c_int32, u8p, C.c_int32, f64p, u8p]),
     "rsd_script_batch": (ci, [vp, u32p, i64p, i32p, i64, u32p, i64p, i32p, i64, i64, ci, u32, ci, i64,

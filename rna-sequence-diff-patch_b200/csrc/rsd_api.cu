@@ -20,6 +20,7 @@
 #include "k_search.cuh"
 #include "k_sim.cuh"
 #include "k_long.cuh"
+#include "k_ingest.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -545,28 +546,106 @@ int rsd_ctx::upload_seqs(SeqBufs &sb, const uint32_t *words, const int64_t *star
     return RSD_OK;
 }
 
-extern "C" int rsd_distance_batch(rsd_ctx *c,
-                                  const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
-                                  const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
-                                  int64_t n_pairs, int64_t max_m_hint, int64_t max_n_hint, int bits, uint32_t symmask, int force_mode,
-                                  double *out, int *mode_out) {
-    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
-    if (n_pairs < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: n_pairs < 0");
-    if (n_pairs > 0 && (!a_words || !a_start || !a_len || !b_words || !b_start || !b_len || !out))
-        return rsd_fail(RSD_EINVAL, "rsd_distance_batch: NULL buffer");
-    RSD_OK_OR_RETURN(c->ensure_device());
-    if (n_pairs == 0) return RSD_OK;
+// One side of a host batch call.  Three input forms:
+//   packed, explicit start[]   words + start + len          (any layout; validated before chunked copies)
+//   packed, canonical          words + len, start == NULL   (rsd_pack layout: start[] is rebuilt on the device)
+//   raw codes                  codes + len                  (1 byte per symbol, concatenated; packed on the device)
+struct SideIn {
+    const uint32_t *words; const int64_t *start; const int32_t *len; int64_t nwords; const uint8_t *codes;
+    bool canonical() const { return codes != nullptr || start == nullptr; }
+};
+
+// block sums of nwords(len) (and of len, for raw codes): base[b] = words before block b, base[nblk] = total
+static void block_bases(const int32_t *len, int64_t n, int sh, int64_t *base, int64_t *sym_base) {
+    const int add = (1 << sh) - 1;
+    int64_t acc = 0, sacc = 0;
+    const int64_t nblk = (n + RSD_SCAN_BLOCK - 1) / RSD_SCAN_BLOCK;
+    for (int64_t b = 0; b < nblk; ++b) {
+        base[b] = acc; if (sym_base) sym_base[b] = sacc;
+        const int64_t e = std::min<int64_t>(n, (b + 1) * RSD_SCAN_BLOCK);
+        int64_t s = 0, ss = 0;
+        for (int64_t p = b * RSD_SCAN_BLOCK; p < e; ++p) { s += (len[p] + add) >> sh; ss += len[p]; }
+        acc += s; sacc += ss;
+    }
+    base[nblk] = acc; if (sym_base) sym_base[nblk] = sacc;
+}
+
+static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_t max_m_hint, int64_t max_n_hint, int bits,
+                         uint32_t symmask, int force_mode, double *out, int *mode_out) {
     const bool trace = getenv("RSD_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_in = now();
     double t_len = 0, t_cost = 0, t_copy = 0, t_comp = 0;
     cudaStream_t st = c->stream, cp = c->copy_stream;
-    const int64_t max_m = max_m_hint > 0 ? max_m_hint : max_len(a_len, n_pairs);
-    const int64_t max_n = max_n_hint > 0 ? max_n_hint : max_len(b_len, n_pairs);
+    const int64_t max_m = max_m_hint > 0 ? max_m_hint : max_len(in[0].len, n_pairs);
+    const int64_t max_n = max_n_hint > 0 ? max_n_hint : max_len(in[1].len, n_pairs);
+    const int sh = bits == 2 ? 4 : 3;
+    const bool any_canon = in[0].canonical() || in[1].canonical();
+    const bool any_codes = in[0].codes || in[1].codes;
+    // costs go up first: a small pageable copy issued later would queue behind the big H2D copies on
+    // the copy engine and stall the first kernel until every chunk has arrived.
+    {
+        ModeInfo mi0;
+        RSD_OK_OR_RETURN(c->classify(symmask, max_m, max_n, bits, force_mode, mi0));
+        RSD_OK_OR_RETURN(c->upload_costs(mi0, st));
+    }
+    t_cost = now();
+    SeqBufs *dS[2] = {&c->bufA, &c->bufB};
+    for (int s = 0; s < 2; ++s) {
+        RSD_OK_OR_RETURN(dS[s]->start.ensure(sizeof(int64_t) * (size_t)n_pairs));
+        RSD_OK_OR_RETURN(dS[s]->len.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    }
+    RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_pairs));
+    // the previous call's kernels may still read these buffers: order the copy stream after them
+    RSD_CUDA(cudaEventRecord(c->ev_sync, st));
+    RSD_CUDA(cudaStreamWaitEvent(cp, c->ev_sync, 0));
+    RSD_CUDA(cudaEventRecord(c->ev_begin, cp));
+    // Lengths of the whole batch go first (8 bytes per pair): every chunk is planned from them right away, so
+    // afterwards the compute streams hold nothing but the chunk kernels.
+    for (int s = 0; s < 2; ++s)
+        RSD_CUDA(cudaMemcpyAsync(dS[s]->len.p, in[s].len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
+    // While the lengths travel: block sums of the canonical sides (the second side on a helper thread).
+    const int64_t nblk = (n_pairs + RSD_SCAN_BLOCK - 1) / RSD_SCAN_BLOCK;
+    int64_t *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [side][0 words, 1 symbols], nblk + 1 entries each
+    int64_t nwords[2] = {in[0].nwords, in[1].nwords};
+    if (any_canon) {
+        const size_t need = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
+        if (need > c->h_stage_cap) {
+            if (c->h_stage) cudaFreeHost(c->h_stage);
+            c->h_stage = nullptr; c->h_stage_cap = 0;
+            RSD_CUDA(cudaMallocHost(&c->h_stage, need + 4096));
+            c->h_stage_cap = need + 4096;
+        }
+        RSD_OK_OR_RETURN(c->d_stage.ensure(need));
+        for (int s = 0; s < 2; ++s) for (int q = 0; q < 2; ++q) tab[s][q] = (int64_t *)c->h_stage + (size_t)(2 * s + q) * (nblk + 1);
+        auto side = [&](int s) { if (in[s].canonical()) block_bases(in[s].len, n_pairs, sh, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
+        if (in[0].canonical() && in[1].canonical() && n_pairs >= (1 << 18)) {
+            std::thread helper(side, 1);
+            side(0);
+            helper.join();
+        } else { side(0); side(1); }
+        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+            if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
+                return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
+                                (long long)in[s].nwords, (long long)tab[s][0][nblk]);
+            nwords[s] = tab[s][0][nblk];
+        }
+        RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, need, cudaMemcpyHostToDevice, cp));
+    }
+    RSD_CUDA(cudaEventRecord(c->ev_len, cp));
+    t_len = now();
+    for (int s = 0; s < 2; ++s) {
+        RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
+        RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
+        if (in[s].codes) {
+            RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
+            RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
+        }
+    }
+    if (any_codes) { RSD_OK_OR_RETURN(c->misc.ensure(64)); RSD_CUDA(cudaMemsetAsync(c->misc.p, 0, 64, st)); }
     // Large batches are cut into chunks of pairs so the H2D copy of chunk k+1 (copy stream) overlaps
     // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
     // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
-    t_len = now();
     // Chunk sizes grow geometrically so the first copy is short; the growth stays below the compute/copy time
     // ratio so that no later chunk waits for its data.
     int n_chunks = 1;
@@ -580,67 +659,57 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
         double wsum = 0, w = 1.0, acc = 0;
         for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= ratio; }
         w = 1.0;
-        for (int k = 0; k < n_chunks; ++k) { acc += w; w *= ratio; bounds[k + 1] = (int64_t)((double)n_pairs * acc / wsum); }
+        for (int k = 0; k < n_chunks; ++k) {
+            acc += w; w *= ratio;
+            int64_t b = (int64_t)((double)n_pairs * acc / wsum);
+            if (any_canon) b = b / RSD_SCAN_BLOCK * RSD_SCAN_BLOCK;           // word offsets are known at block boundaries
+            bounds[k + 1] = std::max(b, bounds[k]);
+        }
     }
     bounds[n_chunks] = n_pairs;
-    // chunked copies need the sequences stored in pair order (what rsd_pack writes); when the chunk
-    // boundaries say otherwise (e.g. one sequence shared by many pairs) copy everything first
-    // A chunk's copy is the word range [start[p0], start[p1]): that is only right when every sequence of the chunk
-    // lies inside it, i.e. when sequence p ends at or before the start of sequence p+1 for every p (one branch-free
-    // pass over start[] and len[], vectorised by the compiler; ~0.3 ms per 10^6 pairs and side).
-    if (n_chunks > 1 && (!pair_ordered(a_start, a_len, n_pairs, a_nwords, bits) || !pair_ordered(b_start, b_len, n_pairs, b_nwords, bits))) {
-        n_chunks = 1; bounds[1] = n_pairs;
-    }
-    const bool whole = n_chunks == 1;
-    // costs go up first: a small pageable copy issued later would queue behind the big H2D copies on
-    // the copy engine and stall the first kernel until every chunk has arrived.
-    {
-        ModeInfo mi0;
-        RSD_OK_OR_RETURN(c->classify(symmask, max_m, max_n, bits, force_mode, mi0));
-        RSD_OK_OR_RETURN(c->upload_costs(mi0, st));
-    }
-    t_cost = now();
-    SeqBufs &dA = c->bufA, &dB = c->bufB;
-    RSD_OK_OR_RETURN(dA.words.ensure(sizeof(uint32_t) * (size_t)(a_nwords + 8)));
-    RSD_OK_OR_RETURN(dA.start.ensure(sizeof(int64_t) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(dA.len.ensure(sizeof(int32_t) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(dB.words.ensure(sizeof(uint32_t) * (size_t)(b_nwords + 8)));
-    RSD_OK_OR_RETURN(dB.start.ensure(sizeof(int64_t) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(dB.len.ensure(sizeof(int32_t) * (size_t)n_pairs));
-    RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_pairs));
-    RSD_CUDA(cudaMemsetAsync((uint32_t *)dA.words.p + a_nwords, 0, sizeof(uint32_t) * 8, cp));
-    RSD_CUDA(cudaMemsetAsync((uint32_t *)dB.words.p + b_nwords, 0, sizeof(uint32_t) * 8, cp));
-    // the previous call's kernels may still read these buffers: order the copy stream after them
-    RSD_CUDA(cudaEventRecord(c->ev_sync, st));
-    RSD_CUDA(cudaStreamWaitEvent(cp, c->ev_sync, 0));
-    RSD_CUDA(cudaEventRecord(c->ev_begin, cp));
-    const bool timing = c->timing;
-    float kernel_ms = 0.f;
-    // Lengths of the whole batch go first (8 bytes per pair): every chunk is planned from them right away, so
-    // afterwards the compute streams hold nothing but the chunk kernels.
-    RSD_CUDA(cudaMemcpyAsync(dA.len.p, a_len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
-    RSD_CUDA(cudaMemcpyAsync(dB.len.p, b_len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
-    RSD_CUDA(cudaEventRecord(c->ev_len, cp));
+    // A chunk's copy is the word range [start[p0], start[p1]): with caller-supplied offsets that is only right when
+    // every sequence of the chunk lies inside it, i.e. when sequence p ends at or before the start of sequence p+1
+    // for every p (one branch-free pass over start[] and len[]; ~0.7 ms per 10^6 pairs and side — callers that
+    // hold rsd_pack's layout pass start == NULL and skip it).  Otherwise the whole batch is copied first.
+    for (int s = 0; s < 2 && n_chunks > 1; ++s)
+        if (!in[s].canonical() && !pair_ordered(in[s].start, in[s].len, n_pairs, in[s].nwords, bits)) { n_chunks = 1; bounds[1] = n_pairs; }
+    auto word_at = [&](int s, int64_t p) -> int64_t {
+        if (p >= n_pairs) return nwords[s];
+        return in[s].canonical() ? tab[s][0][p / RSD_SCAN_BLOCK] : in[s].start[p];
+    };
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
-        const int64_t aw0 = whole ? 0 : a_start[p0], aw1 = (whole || p1 >= n_pairs) ? a_nwords : a_start[p1];
-        const int64_t bw0 = whole ? 0 : b_start[p0], bw1 = (whole || p1 >= n_pairs) ? b_nwords : b_start[p1];
-        RSD_CUDA(cudaMemcpyAsync((uint32_t *)dA.words.p + aw0, a_words + aw0, sizeof(uint32_t) * (size_t)(aw1 - aw0), cudaMemcpyHostToDevice, cp));
-        RSD_CUDA(cudaMemcpyAsync((uint32_t *)dB.words.p + bw0, b_words + bw0, sizeof(uint32_t) * (size_t)(bw1 - bw0), cudaMemcpyHostToDevice, cp));
-        RSD_CUDA(cudaMemcpyAsync((int64_t *)dA.start.p + p0, a_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
-        RSD_CUDA(cudaMemcpyAsync((int64_t *)dB.start.p + p0, b_start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        for (int s = 0; s < 2; ++s) {
+            if (in[s].codes) {
+                const int64_t s0 = tab[s][1][p0 / RSD_SCAN_BLOCK], s1 = p1 >= n_pairs ? tab[s][1][nblk] : tab[s][1][p1 / RSD_SCAN_BLOCK];
+                if (s1 > s0) RSD_CUDA(cudaMemcpyAsync((uint8_t *)c->raw_codes[s].p + s0, in[s].codes + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cp));
+                continue;
+            }
+            const int64_t w0 = n_chunks == 1 ? 0 : word_at(s, p0), w1 = n_chunks == 1 ? nwords[s] : word_at(s, p1);
+            if (w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
+            if (!in[s].canonical())
+                RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        }
         RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
     }
     t_copy = now();
+    const bool timing = c->timing;
+    float kernel_ms = 0.f;
     struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
     c->costs_preloaded = true;
     RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
+    for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+        const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
+        k_starts_from_len<<<(unsigned)nblk, 1024, 0, st>>>((const int32_t *)dS[s]->len.p, n_pairs, sh, dtab, (int64_t *)dS[s]->start.p,
+                                                          in[s].codes ? dtab + (nblk + 1) : nullptr, in[s].codes ? (int64_t *)c->sym_start[s].p : nullptr);
+        c->launches += 1;
+    }
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
         c->cur_slot = k;
-        RSD_OK_OR_RETURN(c->distance_plan((const int32_t *)dA.len.p + p0, (const int32_t *)dB.len.p + p0, p1 - p0, max_m, max_n, bits,
+        RSD_OK_OR_RETURN(c->distance_plan((const int32_t *)dS[0]->len.p + p0, (const int32_t *)dS[1]->len.p + p0, p1 - p0, max_m, max_n, bits,
                                           symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st));
     }
     RSD_CUDA(cudaEventRecord(c->ev_plans, st));
@@ -653,22 +722,40 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
         cudaStream_t sk = (k & 1) ? c->stream2 : st;
         c->cur_slot = k;
         RSD_CUDA(cudaStreamWaitEvent(sk, c->ev_chunk[k], 0));
+        for (int s = 0; s < 2; ++s) if (in[s].codes) {                  // raw codes of the chunk -> packed words, on the device
+            const int64_t w0 = word_at(s, p0), w1 = word_at(s, p1);
+            if (w1 <= w0) continue;
+            const unsigned grid = (unsigned)((w1 - w0 + 255) / 256);
+            unsigned long long *bad = (unsigned long long *)c->misc.p;
+            if (bits == 2) k_pack_codes<2><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
+                                                               (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, bad, (uint32_t *)(bad + 1));
+            else k_pack_codes<4><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
+                                                      (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, bad, (uint32_t *)(bad + 1));
+            c->launches += 1;
+        }
         c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k];
-        RSD_OK_OR_RETURN(c->distance_launch((const uint32_t *)dA.words.p, (const int64_t *)dA.start.p + p0, (const int32_t *)dA.len.p + p0,
-                                            (const uint32_t *)dB.words.p, (const int64_t *)dB.start.p + p0, (const int32_t *)dB.len.p + p0,
+        RSD_OK_OR_RETURN(c->distance_launch((const uint32_t *)dS[0]->words.p, (const int64_t *)dS[0]->start.p + p0, (const int32_t *)dS[0]->len.p + p0,
+                                            (const uint32_t *)dS[1]->words.p, (const int64_t *)dS[1]->start.p + p0, (const int32_t *)dS[1]->len.p + p0,
                                             max_m, bits, (double *)c->out_f64.p + p0, sk));
         // results go back on their own stream, behind nothing but the chunk's kernel
         RSD_CUDA(cudaEventRecord(c->ev_done[k], sk));
         RSD_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
         RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
+    unsigned long long bad_host[2] = {0ull, 0ull};
+    if (any_codes) {
+        // the d2h stream already waits for every chunk's kernels (ev_done[k] above), pack kernels included
+        RSD_CUDA(cudaMemcpyAsync(bad_host, c->misc.p, sizeof bad_host, cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
     t_comp = now();
     RSD_CUDA(cudaStreamSynchronize(c->d2h_stream));
     RSD_CUDA(cudaStreamSynchronize(cp));
     RSD_CUDA(cudaStreamSynchronize(c->stream2));
     RSD_CUDA(cudaStreamSynchronize(st));
-    if (trace) fprintf(stderr, "[rsd trace] host ms: max_len %.3f, classify+costs %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
-                       t_len - t_in, t_cost - t_len, t_copy - t_cost, t_comp - t_copy, now() - t_comp);
+    if (bad_host[0])
+        return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a symbol code of sequence %llu does not fit %d bits", bad_host[0] - 1ull, bits);
+    if (trace) fprintf(stderr, "[rsd trace] host ms: classify+costs %.3f, lengths+block sums %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
+                       t_cost - t_in, t_len - t_cost, t_copy - t_len, t_comp - t_copy, now() - t_comp);
     if (timing) {
         for (int k = 0; k < n_chunks; ++k) {
             if (bounds[k + 1] <= bounds[k]) continue;
@@ -677,8 +764,9 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
             kernel_ms += ms;
         }
         c->timed = false; c->last_ms_override = kernel_ms;
-        if (getenv("RSD_TRACE")) {
+        if (trace) {
             for (int k = 0; k < n_chunks; ++k) {
+                if (bounds[k + 1] <= bounds[k]) continue;
                 float a = 0, b = 0, d = 0;
                 cudaEventElapsedTime(&a, c->ev_begin, c->ev_chunk[k]);
                 cudaEventElapsedTime(&b, c->ev_begin, c->ev_t0[k]);
@@ -689,6 +777,40 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
         }
     }
     return RSD_OK;
+}
+
+extern "C" int rsd_distance_batch(rsd_ctx *c,
+                                  const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
+                                  const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
+                                  int64_t n_pairs, int64_t max_m_hint, int64_t max_n_hint, int bits, uint32_t symmask, int force_mode,
+                                  double *out, int *mode_out) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_pairs < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: n_pairs < 0");
+    if (n_pairs > 0 && (!a_words || !a_len || !b_words || !b_len || !out))
+        return rsd_fail(RSD_EINVAL, "rsd_distance_batch: NULL buffer");
+    if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (n_pairs == 0) return RSD_OK;
+    const SideIn in[2] = {{a_words, a_start, a_len, a_nwords, nullptr}, {b_words, b_start, b_len, b_nwords, nullptr}};
+    return distance_host(c, in, n_pairs, max_m_hint, max_n_hint, bits, symmask, force_mode, out, mode_out);
+}
+
+extern "C" int rsd_distance_batch_codes(rsd_ctx *c, const uint8_t *a_codes, const int32_t *a_len,
+                                        const uint8_t *b_codes, const int32_t *b_len, int64_t n_pairs,
+                                        int64_t max_m_hint, int64_t max_n_hint, int bits, uint32_t symmask, int force_mode,
+                                        double *out, int *mode_out) {
+    if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
+    if (n_pairs < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: n_pairs < 0");
+    if (n_pairs > 0 && (!a_codes || !a_len || !b_codes || !b_len || !out))
+        return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: NULL buffer");
+    if (bits != 2 && bits != 4) return rsd_fail(RSD_EINVAL, "rsd: bits must be 2 or 4");
+    if (symmask == 0) symmask = bits == 2 ? 0xFu : 0x7FFFu;              // unknown: every symbol the packing can hold
+    if (bits == 2 && (symmask & ~0xFu)) return rsd_fail(RSD_EINVAL, "rsd: 2-bit packing with symbols outside ACGU");
+    RSD_OK_OR_RETURN(c->ensure_device());
+    if (n_pairs == 0) return RSD_OK;
+    for (int64_t p = 0; p < n_pairs; ++p) if ((a_len[p] | b_len[p]) < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: negative length at pair %lld", (long long)p);
+    const SideIn in[2] = {{nullptr, nullptr, a_len, 0, a_codes}, {nullptr, nullptr, b_len, 0, b_codes}};
+    return distance_host(c, in, n_pairs, max_m_hint, max_n_hint, bits, symmask, force_mode, out, mode_out);
 }
 
 // ------------------------------------------------------------------------------------------------

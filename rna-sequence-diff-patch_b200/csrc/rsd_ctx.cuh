@@ -91,6 +91,10 @@ struct rsd_ctx {
 
     SeqBufs bufA, bufB, bufX, bufQ;
     DevBuf out_f64;
+    // host batch calls with a canonical layout / raw codes: block-offset tables (pinned staging + device copy),
+    // raw code bytes and symbol offsets per side
+    void *h_stage = nullptr; size_t h_stage_cap = 0;
+    DevBuf d_stage, raw_codes[2], sym_start[2];
     PlanSlot slots[RSD_MAX_CHUNKS];
     int cur_slot = 0;
     PlanSlot &ps() { return slots[cur_slot]; }
@@ -134,5 +138,7 @@ struct rsd_ctx {
                          &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
                          &db_dist, &db_topi, &db_tops, &db_aux, &db_perm, &sim_q, &sim_scores, &sim_aux, &sim_codes, &sim_work};
         for (DevBuf *b : all) b->release();
+        d_stage.release(); for (int s = 0; s < 2; ++s) { raw_codes[s].release(); sym_start[s].release(); }
+        if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; h_stage_cap = 0; }
     }
 };

@@ -40,7 +40,8 @@ def slice_packed(p: PackedSeqs, lo: int, hi: int) -> PackedSeqs:
     w0 = int(p.start[lo])
     w1 = int(p.start[hi - 1]) + (int(p.len[hi - 1]) + per - 1) // per
     words = np.concatenate([p.words[w0:w1], np.zeros(4, np.uint32)])
-    return PackedSeqs(words, (p.start[lo:hi] - w0).astype(np.int64), p.len[lo:hi].copy(), p.bits, p.symmask)
+    return PackedSeqs(words, (p.start[lo:hi] - w0).astype(np.int64), p.len[lo:hi].copy(), p.bits, p.symmask,
+                      canonical=p.canonical)
 
 
 def gather_merge(local_idx: np.ndarray, local_score: np.ndarray, group=None, device=None):

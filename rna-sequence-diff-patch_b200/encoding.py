@@ -55,6 +55,7 @@ class PackedSeqs:
     len: np.ndarray      # int32 [n]
     bits: int            # 2 or 4
     symmask: int         # bit c set = code c present
+    canonical: bool = False   # rsd_pack's layout (start[p] = words of the sequences before p): start[] can stay on the host
 
     @property
     def n(self) -> int:
@@ -93,7 +94,7 @@ def pack(seqs, bits: int | None = None) -> PackedSeqs:
     _lib.check(lib.rsd_pack(_lib.ptr(codes, C.c_uint8), _lib.ptr(off, C.c_int64), n, bits,
                             _lib.ptr(words, C.c_uint32), _lib.ptr(start, C.c_int64),
                             _lib.ptr(out_len, C.c_int32), C.byref(mask)))
-    return PackedSeqs(words, start, out_len, bits, int(mask.value))
+    return PackedSeqs(words, start, out_len, bits, int(mask.value), canonical=True)
 
 
 def unpack(p: PackedSeqs):

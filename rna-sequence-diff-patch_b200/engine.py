@@ -82,10 +82,31 @@ class Engine:
         if out is None:
             out = np.zeros(A.n, dtype=np.float64)
         mode = C.c_int()
+        # a batch in rsd_pack's layout keeps its start[] on the host: the device rebuilds it from the lengths
         check(self._lib.rsd_distance_batch(
-            self._ctx, ptr(A.words, _u32), ptr(A.start, _i64), ptr(A.len, _i32), A.words.shape[0],
-            ptr(B.words, _u32), ptr(B.start, _i64), ptr(B.len, _i32), B.words.shape[0],
+            self._ctx, ptr(A.words, _u32), None if A.canonical else ptr(A.start, _i64), ptr(A.len, _i32), A.words.shape[0],
+            ptr(B.words, _u32), None if B.canonical else ptr(B.start, _i64), ptr(B.len, _i32), B.words.shape[0],
             A.n, A.max_len, B.max_len, bits, A.symmask | B.symmask, force_mode, ptr(out, _f64), C.byref(mode)))
+        self.last_mode = mode.value
+        return out
+
+    def distance_batch_codes(self, a_codes: np.ndarray, a_len: np.ndarray, b_codes: np.ndarray, b_len: np.ndarray,
+                             bits: int = 4, symmask: int = 0, force_mode: int = 0, out: np.ndarray | None = None):
+        """Distances straight from raw symbol codes (uint8, sequences concatenated in pair order) and int32
+        lengths: the codes are packed on the device, chunk by chunk, under the kernels of earlier chunks."""
+        n = int(a_len.shape[0])
+        if int(b_len.shape[0]) != n:
+            raise ValueError("a_len and b_len must have the same length")
+        a_codes = np.ascontiguousarray(a_codes, np.uint8); b_codes = np.ascontiguousarray(b_codes, np.uint8)
+        a_len = np.ascontiguousarray(a_len, np.int32); b_len = np.ascontiguousarray(b_len, np.int32)
+        if out is None:
+            out = np.zeros(n, dtype=np.float64)
+        pad = np.zeros(1, np.uint8)
+        mode = C.c_int()
+        check(self._lib.rsd_distance_batch_codes(
+            self._ctx, ptr(a_codes if a_codes.size else pad, _u8), ptr(a_len, _i32),
+            ptr(b_codes if b_codes.size else pad, _u8), ptr(b_len, _i32), n,
+            int(a_len.max(initial=0)), int(b_len.max(initial=0)), bits, symmask, force_mode, ptr(out, _f64), C.byref(mode)))
         self.last_mode = mode.value
         return out
 

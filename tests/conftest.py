@@ -27,3 +27,29 @@ def default_costs(golden):
 @pytest.fixture(scope="session")
 def user_costs(golden):
     return golden["user_costs"]
+
+
+@pytest.fixture(scope="session")
+def dropin(golden, tmp_path_factory):
+    """The drop-in modules imported the way the reference's are: from a working directory that holds costs.json
+    and user_costs.json (SED:6-18 reads them from the CWD at import), drop-in directory first on sys.path."""
+    drop = os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin")
+    work = tmp_path_factory.mktemp("refcwd")
+    with open(work / "costs.json", "w") as f:
+        json.dump(golden["default_costs"], f)
+    with open(work / "user_costs.json", "w") as f:
+        json.dump(golden["user_costs"], f)
+    cwd = os.getcwd()
+    os.chdir(work)
+    sys.path.insert(0, drop)
+    try:
+        for name in ("StringEditDistance", "IRMethods"):
+            sys.modules.pop(name, None)
+        import StringEditDistance
+        import IRMethods
+    finally:
+        os.chdir(cwd)
+
+    class Mods:
+        SED, IR, cwd = StringEditDistance, IRMethods, str(work)
+    return Mods

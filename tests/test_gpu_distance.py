@@ -38,12 +38,11 @@ def oracle_batch(a, b, costs):
     return O.distance_batch(ac, ao, bc, bo, costs)
 
 
-def test_dropin_golden_matrices(R, golden):
-    sys.path.insert(0, os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+def test_dropin_golden_matrices(R, golden, dropin):
     cwd = os.getcwd()
-    os.chdir(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    os.chdir(dropin.cwd)
     try:
-        import StringEditDistance as S
+        S = dropin.SED
         assert S.default_costs == golden["default_costs"] and S.user_costs == golden["user_costs"]
         dp = S.wagnerFisher('AGRGA', 'AGGGAA', True)
         assert str(dp) == golden["G1"]["dp_str"]
@@ -197,12 +196,11 @@ def test_large_batch_property_identity_and_symmetry(R, eng, golden):
     assert np.array_equal(d_ab[sub], want)
 
 
-def test_wf_score_and_search_collection_g7(R, golden):
-    sys.path.insert(0, os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+def test_wf_score_and_search_collection_g7(R, golden, dropin):
     cwd = os.getcwd()
-    os.chdir(os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin"))
+    os.chdir(dropin.cwd)
     try:
-        import IRMethods as IR
+        IR = dropin.IR
 
         class Coll:
             def __init__(self, docs): self.docs = docs
@@ -244,9 +242,92 @@ def test_shared_sequence_layout_falls_back_to_whole_copy(R, eng, golden):
         eng.ctx, _lib.ptr(Q.words, C.c_uint32), _lib.ptr(a_start, C.c_int64), _lib.ptr(a_len, C.c_int32), Q.words.shape[0],
         _lib.ptr(B.words, C.c_uint32), _lib.ptr(B.start, C.c_int64), _lib.ptr(B.len, C.c_int32), B.words.shape[0],
         n, len(q), 40, 2, 0xF, 0, _lib.ptr(out, C.c_double), C.byref(mode)))
-    sub = rng.choice(n, size=300, replace=False)
-    want = oracle_batch([q] * 300, [b[k] for k in sub], golden["default_costs"])
-    assert np.array_equal(out[sub], want)
+    want = oracle_batch([q] * n, b, golden["default_costs"])
+    assert np.array_equal(out, want)
+    # sequences stored in REVERSE pair order: start[] is monotone at no chunk boundary either
+    order = np.arange(n)[::-1]
+    Br = R.pack([b[k] for k in order])
+    b_start = Br.start[order].copy(); b_len = Br.len[order].copy()
+    A = R.pack([q] * n)
+    out2 = np.zeros(n)
+    _lib.check(R.load_library().rsd_distance_batch(
+        eng.ctx, _lib.ptr(A.words, C.c_uint32), None, _lib.ptr(A.len, C.c_int32), A.words.shape[0],
+        _lib.ptr(Br.words, C.c_uint32), _lib.ptr(b_start, C.c_int64), _lib.ptr(b_len, C.c_int32), Br.words.shape[0],
+        n, len(q), 40, 2, 0xF, 0, _lib.ptr(out2, C.c_double), C.byref(mode)))
+    assert np.array_equal(out2, want)
+
+
+def test_canonical_layout_without_start_equals_explicit_start(R, eng, golden):
+    """start == NULL (rsd_pack's layout, offsets rebuilt on the device) vs caller-supplied start[]: same distances;
+    lengths 0 and exact word multiples included, batch large enough for the chunked copies."""
+    import ctypes as C
+    from rna_sequence_diff_patch_b200 import _lib
+    rng = np.random.default_rng(18)
+    n = 150_001
+    la = rng.integers(0, 70, size=n); lb = rng.integers(0, 70, size=n)
+    la[rng.random(n) < 0.05] = 0; lb[rng.random(n) < 0.05] = 32; la[:3] = [16, 0, 0]; lb[-2:] = [0, 0]
+    oa = np.zeros(n + 1, np.int64); np.cumsum(la, out=oa[1:]); ob = np.zeros(n + 1, np.int64); np.cumsum(lb, out=ob[1:])
+    for alpha, table in ((4, "user_costs"), (15, "default_costs")):
+        ca = rng.integers(0, alpha, size=int(oa[-1]), dtype=np.uint8); cb = rng.integers(0, alpha, size=int(ob[-1]), dtype=np.uint8)
+        costs = golden[table]
+        eng.set_costs(costs)
+        A, B = R.pack((ca, oa)), R.pack((cb, ob))
+        assert A.canonical and B.canonical
+        got = eng.distance_batch(A, B)                                  # start == NULL on both sides
+        want = O.distance_batch(ca, oa, cb, ob, costs)
+        assert np.array_equal(got, want)
+        A.canonical = False                                             # explicit start on one side, NULL on the other
+        assert np.array_equal(eng.distance_batch(A, B), want)
+        # lengths that need more words than the buffer holds are refused
+        mode = C.c_int(); out = np.zeros(n)
+        rc = R.load_library().rsd_distance_batch(
+            eng.ctx, _lib.ptr(A.words, C.c_uint32), None, _lib.ptr(A.len, C.c_int32), A.words.shape[0] - 40,
+            _lib.ptr(B.words, C.c_uint32), None, _lib.ptr(B.len, C.c_int32), B.words.shape[0],
+            n, 0, 0, A.bits, A.symmask | B.symmask, 0, _lib.ptr(out, C.c_double), C.byref(mode))
+        assert rc == _lib.RSD_EINVAL
+
+
+@pytest.mark.parametrize("n", [1, 4097, 200_003])
+def test_distance_from_raw_codes_packs_on_the_device(R, eng, golden, n):
+    """rsd_distance_batch_codes: 1 byte per symbol in, packed by k_pack_codes chunk by chunk == the oracle."""
+    rng = np.random.default_rng(19 + n)
+    la = rng.integers(0, 90, size=n).astype(np.int32); lb = rng.integers(0, 90, size=n).astype(np.int32)
+    la[rng.random(n) < 0.03] = 0; lb[rng.random(n) < 0.03] = 0
+    oa = np.zeros(n + 1, np.int64); np.cumsum(la, out=oa[1:]); ob = np.zeros(n + 1, np.int64); np.cumsum(lb, out=ob[1:])
+    for alpha, bits, table, mode in ((4, 2, "user_costs", 1), (4, 4, "default_costs", 2), (15, 4, "default_costs", 3)):
+        ca = rng.integers(0, alpha, size=int(oa[-1]), dtype=np.uint8); cb = rng.integers(0, alpha, size=int(ob[-1]), dtype=np.uint8)
+        costs = golden[table]
+        eng.set_costs(costs)
+        got = eng.distance_batch_codes(ca, la, cb, lb, bits=bits, symmask=0xF if alpha == 4 else 0)
+        assert eng.last_mode == mode
+        assert np.array_equal(got, O.distance_batch(ca, oa, cb, ob, costs))
+    if n > 1000:
+        bad = ca.copy(); bad[int(oa[n // 2]) + 1 if la[n // 2] > 1 else 0] = 9
+        with pytest.raises(R.RsdError):
+            eng.distance_batch_codes(bad % 16, la, cb % 4, lb, bits=2)
+
+
+def test_plan_slots_start_clean_on_recycled_device_memory(R, golden):
+    """The plan's privatised bin counters must be zeroed by the library, not by luck: fill a large part of the
+    device with 0xFF, release it, then let a NEW context allocate its plan slots (chunked call: slots 0..4)."""
+    import torch
+    junk = [torch.full((1 << 28,), -1, dtype=torch.int32, device="cuda") for _ in range(8)]       # 8 GiB of 0xFF
+    torch.cuda.synchronize()
+    del junk
+    torch.cuda.empty_cache()
+    eng2 = R.Engine(0)
+    try:
+        rng = np.random.default_rng(20)
+        a = rand_seqs(rng, 80000, 30, 90, "AGCU"); b = rand_seqs(rng, 80000, 30, 90, "AGCU")
+        eng2.set_costs(golden["user_costs"])
+        got = eng2.distance_batch(R.pack(a), R.pack(b))
+        assert np.array_equal(got, oracle_batch(a, b, golden["user_costs"]))
+        res = eng2.script_batch(R.pack(a[:3000]), R.pack(b[:3000]))
+        ac, ao = O.concat(a[:3000]); bc, bo = O.concat(b[:3000])
+        _, _, _, cnt, dist = O.script_batch(ac, ao, bc, bo, golden["user_costs"])
+        assert np.array_equal(res["n_ops"], cnt) and np.array_equal(res["dist"], dist)
+    finally:
+        eng2.close()
 
 
 def test_pair_list_shards_concatenate_to_the_unsharded_result(R, eng, golden):

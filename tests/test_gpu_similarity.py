@@ -101,15 +101,13 @@ def test_long_records_and_empty_query(R, eng):
         eng.db_free()
 
 
-def test_dropin_search_collection_serves_every_measure(R, gir):
+def test_dropin_search_collection_serves_every_measure(R, gir, dropin):
     """search_collection(query, 'tf', collection, IRMethods.<measure>) == the reference's list, and the measure
     objects called on two sequences give the same numbers (IR:443-477, IR:49-389)."""
-    drop = os.path.join(ROOT, "rna-sequence-diff-patch_b200", "dropin")
-    sys.path.insert(0, drop)
     cwd = os.getcwd()
-    os.chdir(drop)
+    os.chdir(dropin.cwd)
     try:
-        import IRMethods as IR
+        IR = dropin.IR
 
         class Coll:
             def __init__(self, docs): self.docs = docs

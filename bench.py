@@ -128,6 +128,49 @@ def cpu_baseline(ca, oa, cb, ob, costs, target_s=12.0, nthreads=0):
     return cells / dt * 1e-9, cores, f"first {n} pairs of the workload, C oracle port, {cores} threads", dt
 
 
+def _pyref_init(ref_dir):
+    """Pool initialiser: import the unmodified reference once per worker (it reads its cost files from the CWD and
+    prints a self-test at import, SED:6-18,463-471)."""
+    import contextlib
+    import io
+    os.chdir(ref_dir)
+    sys.path.insert(0, ref_dir)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import StringEditDistance  # noqa: F401
+
+
+def _pyref_pair(args):
+    import StringEditDistance as S
+    a, b = args
+    dp = S.wagnerFisher(a, b, True)
+    return float(dp[len(dp) - 1][len(dp[0]) - 1].value)
+
+
+def python_reference_baseline(ca, oa, cb, ob, n_pairs=768, want=None):
+    """The reference's own pure-Python wagnerFisher (baseline/_ref/StringEditDistance.py, unmodified) on the first
+    n_pairs pairs of the workload, one spawn-pool worker per host core; -> dict for the JSON line."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "StringEditDistance.py")):
+        return {"unavailable": "baseline/_ref/StringEditDistance.py is absent (run `python __graft_entry__.py build` where /root/reference exists)"}
+    import multiprocessing as mp
+    sym = np.frombuffer(b"AGCUYRWSKMDVHBN", dtype=np.uint8)
+    pairs = [(sym[ca[oa[p]:oa[p + 1]]].tobytes().decode(), sym[cb[ob[p]:ob[p + 1]]].tobytes().decode()) for p in range(n_pairs)]
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_pyref_init, initargs=(ref_dir,)) as pool:
+        pool.map(_pyref_pair, pairs[:cores])                      # warm: every worker has imported the module
+        t0 = time.perf_counter()
+        got = pool.map(_pyref_pair, pairs, chunksize=1)
+        dt = time.perf_counter() - t0
+    cells = float(((oa[1: n_pairs + 1] - oa[:n_pairs]) * (ob[1: n_pairs + 1] - ob[:n_pairs])).sum())
+    res = {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+           "sample": f"first {n_pairs} pairs of the workload through the unmodified StringEditDistance.wagnerFisher "
+                     f"(pure Python, spawn pool of {cores} workers, {dt:.1f} s)"}
+    if want is not None:
+        res["matches_gpu"] = bool(np.array_equal(np.array(got), want[:n_pairs]))
+    return res
+
+
 def _claim_stdout():
     """Keep stdout for the single JSON line: libraries (NCCL prints its version banner there) get stderr."""
     real = os.fdopen(os.dup(1), "w")
@@ -164,7 +207,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c2-iupac"])
     ap.add_argument("--pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the short C3/C4/C5 side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3/C4/C5 side measurements")
+    ap.add_argument("--c5-records", type=int, default=10_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +241,7 @@ def main():
             "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": "port", "sample": desc,
                              "note": "the reference is pure Python and cannot travel to the GPU box; this is the C "
                                      "restatement of its algorithm (oracle/wf_oracle.c), pinned to it by tests/golden"},
+            "cpu_baseline_python": python_reference_baseline(ca, oa, cb, ob),
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0})])
         return
@@ -349,6 +394,17 @@ def main():
                  "h2d_bytes_per_step": int(hc["ca"].numel() + hc["cb"].numel() + 8 * args.pairs), "d2h_bytes_per_step": d2h,
                  "what": "rsd_distance_batch_codes: 1 byte per symbol from pinned host memory, packed on the device per chunk"}
 
+    # ---- BASELINE config 5 at every N: 10^7-record database sharded over the ranks, ONE all_gather per batch ----
+    c5s = None
+    if not args.no_extras:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs as BC
+            c5s = BC.c5_sharded(eng, rank, world, dev, records=args.c5_records, steps=args.steps, warmup=args.warmup)
+        except Exception as ex:                      # side measurements must never break the contract line
+            c5s = {"error": repr(ex)}
+        eng.set_costs(costs)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,6 +446,9 @@ def main():
         n_chk = 20000
         want = O.distance_batch(ca[: oa[n_chk]], oa[: n_chk + 1].copy(), cb[: ob[n_chk]], ob[: n_chk + 1].copy(), costs)
         assert np.array_equal(check_dev[:n_chk], want), "GPU distances differ from the oracle"
+    cpu_py = None if args.no_cpu_baseline else python_reference_baseline(ca, oa, cb, ob, want=check_dev)
+    if cpu_py is not None and cpu_py.get("matches_gpu") is False:
+        raise AssertionError("GPU distances differ from the unmodified Python reference")
 
     # ---- side measurements of the other BASELINE configs (reduced sizes, N=1 only; full sizes: tools/bench_configs.py)
     extras = None
@@ -397,16 +456,22 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_configs as BC
-            e3 = BC.c3(eng, 20000, reps=2); e4 = BC.c4(eng, reps=2); e5 = BC.c5(eng, 2_000_000, reps=2)
+            e3 = BC.c3(eng, 20000, reps=2); e4 = BC.c4(eng, reps=2); e2i = BC.c2_iupac(eng, 200_000, reps=3)
             extras = {"c3_script_patch_roundtrip": {"pairs": e3["pairs"], "pairs_per_s_device": e3["device_pairs_per_s"],
-                                                    "gcups_device": e3["device_gcups"], "pairs_per_s_e2e_pageable": e3["e2e_pairs_per_s"],
-                                                    "roundtrip_ok": e3["roundtrip_ok"]},
+                                                    "gcups_device": e3["device_gcups"], "pairs_per_s_e2e": e3["e2e_pairs_per_s"],
+                                                    "roundtrip_ok": e3["roundtrip_ok"], "oracle_checked_pairs": e3["oracle_checked_pairs"]},
                       "c4_long_pair_50kb": {"gcups_device": e4["device_gcups"], "ms_device": e4["device_s"] * 1e3,
-                                            "forward_only_ms": e4["forward_only_device_s"] * 1e3, "n_ops": e4["n_ops"]},
-                      "c5_db_search_top10": {"records": e5["records"], "queries": e5["queries"], "gcups_device": e5["device_gcups"],
-                                             "ms_per_query_batch": e5["device_s"] * 1e3}}
+                                            "forward_only_ms": e4["forward_only_device_s"] * 1e3, "n_ops": e4["n_ops"],
+                                            "script_equals_oracle_digest": e4["script_equals_oracle_digest"],
+                                            "roofline_frac_5ops": e4["device_gcups"] * 5e-3 / peak if peak else None},
+                      "c2_iupac_fp64": dict(e2i, roofline_frac_dadd=(e2i["device_gcups"] * 3e-3 / peaks["dadd"]) if peaks.get("dadd") else None,
+                                            note="15-letter alphabet, default costs.json (0.66 / 0.83 ...): fp64 kernel in the reference's "
+                                                 "operation order, 3 DADD per cell against the measured DADD issue peak")}
         except Exception as ex:                      # side measurements must never break the contract line
             extras = {"error": repr(ex)}
+    if c5s and "gcups" in c5s and peak:
+        c5s["roofline_frac_5ops"] = c5s["gcups"] * 5e-3 / peak          # 5 integer ops per cell against the IADD3 issue peak
+        c5s["roofline_frac_1alu_per_cell"] = c5s["gcups"] * 1e-3 / peak  # the kernel's own ceiling: one alu-pipe instruction per cell
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -421,12 +486,12 @@ def main():
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {1: "s16x2", 2: "s32", 3: "f64"}[mode_used], "data": "synthetic",
-        "config": config, "roofline": roofline, "cpu_baseline": cpu,
+        "config": config, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py,
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "e2e_from_codes": e2e_codes,
         "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-        "clocks": sampler.summary(), "other_configs": extras})])
+        "clocks": sampler.summary(), "other_configs": dict(extras or {}, c5_sharded_search=c5s) if (extras or c5s) else None})])
     if world > 1:
         dist.destroy_process_group()
 

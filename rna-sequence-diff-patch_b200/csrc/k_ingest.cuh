@@ -101,7 +101,9 @@ k_pack_codes(const uint8_t *__restrict__ codes, const int64_t *__restrict__ sym_
         }
         words[w] = word;
     }
+    if (mask) {                                                  // optional: which symbols occur
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(RSD_FULL, seen, o);
-    if ((threadIdx.x & 31) == 0 && seen) atomicOr(mask, seen);
+        for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(RSD_FULL, seen, o);
+        if (lane == 0 && seen) atomicOr(mask, seen);
+    }
 }

@@ -80,6 +80,7 @@ int rsd_ctx::ensure_device() {
     RSD_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
     RSD_CUDA(cudaEventCreateWithFlags(&ev_len, cudaEventDisableTiming));
     RSD_CUDA(cudaEventCreateWithFlags(&ev_plans, cudaEventDisableTiming));
+    RSD_CUDA(cudaEventCreateWithFlags(&ev_tab, cudaEventDisableTiming));
     RSD_CUDA(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
     for (int k = 0; k < RSD_MAX_CHUNKS; ++k) RSD_CUDA(cudaEventCreate(&ev_chunk[k]));
     RSD_CUDA(cudaEventCreate(&ev_begin));
@@ -106,7 +107,7 @@ extern "C" int rsd_destroy(rsd_ctx *c) {
         cudaFree(c->d_ic); cudaFree(c->d_fc);
         cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
         cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->d2h_stream);
-        cudaEventDestroy(c->ev_sync); cudaEventDestroy(c->ev_len); cudaEventDestroy(c->ev_plans); cudaEventDestroy(c->ev_begin);
+        cudaEventDestroy(c->ev_sync); cudaEventDestroy(c->ev_len); cudaEventDestroy(c->ev_plans); cudaEventDestroy(c->ev_tab); cudaEventDestroy(c->ev_begin);
         for (int k = 0; k < RSD_MAX_CHUNKS; ++k) { cudaEventDestroy(c->ev_chunk[k]); cudaEventDestroy(c->ev_t0[k]); cudaEventDestroy(c->ev_t1[k]); cudaEventDestroy(c->ev_done[k]); }
     }
     delete c;
@@ -604,56 +605,40 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     // afterwards the compute streams hold nothing but the chunk kernels.
     for (int s = 0; s < 2; ++s)
         RSD_CUDA(cudaMemcpyAsync(dS[s]->len.p, in[s].len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
-    // While the lengths travel: block sums of the canonical sides (the second side on a helper thread).
+    RSD_CUDA(cudaEventRecord(c->ev_len, cp));
+    // While the lengths travel and the plans are enqueued: block sums of the canonical sides on helper threads.
     const int64_t nblk = (n_pairs + RSD_SCAN_BLOCK - 1) / RSD_SCAN_BLOCK;
     int64_t *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [side][0 words, 1 symbols], nblk + 1 entries each
     int64_t nwords[2] = {in[0].nwords, in[1].nwords};
+    const size_t tab_bytes = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
+    std::thread helpers[2];
+    struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 2; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
     if (any_canon) {
-        const size_t need = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
-        if (need > c->h_stage_cap) {
+        if (tab_bytes + 64 > c->h_stage_cap) {
             if (c->h_stage) cudaFreeHost(c->h_stage);
             c->h_stage = nullptr; c->h_stage_cap = 0;
-            RSD_CUDA(cudaMallocHost(&c->h_stage, need + 4096));
-            c->h_stage_cap = need + 4096;
+            RSD_CUDA(cudaMallocHost(&c->h_stage, tab_bytes + 4096));
+            c->h_stage_cap = tab_bytes + 4096;
         }
-        RSD_OK_OR_RETURN(c->d_stage.ensure(need));
+        RSD_OK_OR_RETURN(c->d_stage.ensure(tab_bytes + 64));
         for (int s = 0; s < 2; ++s) for (int q = 0; q < 2; ++q) tab[s][q] = (int64_t *)c->h_stage + (size_t)(2 * s + q) * (nblk + 1);
-        auto side = [&](int s) { if (in[s].canonical()) block_bases(in[s].len, n_pairs, sh, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
-        if (in[0].canonical() && in[1].canonical() && n_pairs >= (1 << 18)) {
-            std::thread helper(side, 1);
-            side(0);
-            helper.join();
-        } else { side(0); side(1); }
         for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-            if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
-                return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
-                                (long long)in[s].nwords, (long long)tab[s][0][nblk]);
-            nwords[s] = tab[s][0][nblk];
-        }
-        RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, need, cudaMemcpyHostToDevice, cp));
-    }
-    RSD_CUDA(cudaEventRecord(c->ev_len, cp));
-    t_len = now();
-    for (int s = 0; s < 2; ++s) {
-        RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
-        RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
-        if (in[s].codes) {
-            RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
-            RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
+            auto job = [&in, &tab, n_pairs, sh, s] { block_bases(in[s].len, n_pairs, sh, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
+            if (n_pairs >= (1 << 17)) helpers[s] = std::thread(job); else job();
         }
     }
-    if (any_codes) { RSD_OK_OR_RETURN(c->misc.ensure(64)); RSD_CUDA(cudaMemsetAsync(c->misc.p, 0, 64, st)); }
     // Large batches are cut into chunks of pairs so the H2D copy of chunk k+1 (copy stream) overlaps
     // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
     // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
-    // Chunk sizes grow geometrically so the first copy is short; the growth stays below the compute/copy time
-    // ratio so that no later chunk waits for its data.
+    // Packed input: chunk sizes grow geometrically so the first copy is short; the growth stays below the
+    // compute/copy time ratio so that no later chunk waits for its data.  Raw codes are four times the bytes and
+    // copy-bound: equal chunks, so that little work is left when the last byte has arrived.
     int n_chunks = 1;
     int64_t bounds[RSD_MAX_CHUNKS + 1];
     bounds[0] = 0;
     if (n_pairs >= (1 << 16)) {
-        n_chunks = 5;
-        double ratio = 1.5;
+        n_chunks = any_codes ? 16 : 5;
+        double ratio = any_codes ? 1.0 : 1.5;
         if (const char *e = getenv("RSD_CHUNKS")) n_chunks = std::min(std::max(atoi(e), 1), RSD_MAX_CHUNKS);
         if (const char *e = getenv("RSD_CHUNK_RATIO")) ratio = std::max(atof(e), 1.0);
         double wsum = 0, w = 1.0, acc = 0;
@@ -669,10 +654,51 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     bounds[n_chunks] = n_pairs;
     // A chunk's copy is the word range [start[p0], start[p1]): with caller-supplied offsets that is only right when
     // every sequence of the chunk lies inside it, i.e. when sequence p ends at or before the start of sequence p+1
-    // for every p (one branch-free pass over start[] and len[]; ~0.7 ms per 10^6 pairs and side — callers that
+    // for every p (one branch-free pass over start[] and len[]; ~1 ms per 10^6 pairs and side — callers that
     // hold rsd_pack's layout pass start == NULL and skip it).  Otherwise the whole batch is copied first.
     for (int s = 0; s < 2 && n_chunks > 1; ++s)
         if (!in[s].canonical() && !pair_ordered(in[s].start, in[s].len, n_pairs, in[s].nwords, bits)) { n_chunks = 1; bounds[1] = n_pairs; }
+    t_len = now();
+    const bool timing = c->timing;
+    float kernel_ms = 0.f;
+    struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
+    c->costs_preloaded = true;
+    RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
+    auto enqueue_plans = [&]() -> int {
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+            if (p1 <= p0) continue;
+            c->cur_slot = k;
+            RSD_OK_OR_RETURN(c->distance_plan((const int32_t *)dS[0]->len.p + p0, (const int32_t *)dS[1]->len.p + p0, p1 - p0, max_m, max_n, bits,
+                                              symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st));
+        }
+        c->cur_slot = 0;
+        return RSD_OK;
+    };
+    // packed input is compute-bound: the plans are enqueued while the helper threads sum; raw codes are copy-bound:
+    // there the copies go out first
+    if (!any_codes) RSD_OK_OR_RETURN(enqueue_plans());
+    const double t_plans = now();
+    // the block sums are needed from here on
+    for (int s = 0; s < 2; ++s) if (helpers[s].joinable()) helpers[s].join();
+    for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+        if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
+            return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
+                            (long long)in[s].nwords, (long long)tab[s][0][nblk]);
+        nwords[s] = tab[s][0][nblk];
+    }
+    if (any_canon) RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, tab_bytes, cudaMemcpyHostToDevice, cp));
+    RSD_CUDA(cudaEventRecord(c->ev_tab, cp));
+    for (int s = 0; s < 2; ++s) {
+        RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
+        RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
+        if (in[s].codes) {
+            RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
+            RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
+        }
+    }
+    unsigned long long *d_bad = (unsigned long long *)((unsigned char *)c->d_stage.p + tab_bytes);       // {bad sequence + 1, symbols seen}
+    if (any_codes) RSD_CUDA(cudaMemsetAsync(d_bad, 0, 16, st));
     auto word_at = [&](int s, int64_t p) -> int64_t {
         if (p >= n_pairs) return nwords[s];
         return in[s].canonical() ? tab[s][0][p / RSD_SCAN_BLOCK] : in[s].start[p];
@@ -694,23 +720,15 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
     }
     t_copy = now();
-    const bool timing = c->timing;
-    float kernel_ms = 0.f;
-    struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
-    c->costs_preloaded = true;
-    RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
-    for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-        const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
-        k_starts_from_len<<<(unsigned)nblk, 1024, 0, st>>>((const int32_t *)dS[s]->len.p, n_pairs, sh, dtab, (int64_t *)dS[s]->start.p,
-                                                          in[s].codes ? dtab + (nblk + 1) : nullptr, in[s].codes ? (int64_t *)c->sym_start[s].p : nullptr);
-        c->launches += 1;
-    }
-    for (int k = 0; k < n_chunks; ++k) {
-        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
-        if (p1 <= p0) continue;
-        c->cur_slot = k;
-        RSD_OK_OR_RETURN(c->distance_plan((const int32_t *)dS[0]->len.p + p0, (const int32_t *)dS[1]->len.p + p0, p1 - p0, max_m, max_n, bits,
-                                          symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st));
+    if (any_codes) RSD_OK_OR_RETURN(enqueue_plans());
+    if (any_canon) {
+        RSD_CUDA(cudaStreamWaitEvent(st, c->ev_tab, 0));
+        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+            const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
+            k_starts_from_len<<<(unsigned)nblk, 1024, 0, st>>>((const int32_t *)dS[s]->len.p, n_pairs, sh, dtab, (int64_t *)dS[s]->start.p,
+                                                              in[s].codes ? dtab + (nblk + 1) : nullptr, in[s].codes ? (int64_t *)c->sym_start[s].p : nullptr);
+            c->launches += 1;
+        }
     }
     RSD_CUDA(cudaEventRecord(c->ev_plans, st));
     RSD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_plans, 0));
@@ -726,11 +744,10 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
             const int64_t w0 = word_at(s, p0), w1 = word_at(s, p1);
             if (w1 <= w0) continue;
             const unsigned grid = (unsigned)((w1 - w0 + 255) / 256);
-            unsigned long long *bad = (unsigned long long *)c->misc.p;
             if (bits == 2) k_pack_codes<2><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
-                                                               (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, bad, (uint32_t *)(bad + 1));
+                                                               (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
             else k_pack_codes<4><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
-                                                      (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, bad, (uint32_t *)(bad + 1));
+                                                      (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
             c->launches += 1;
         }
         c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k];
@@ -742,20 +759,18 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         RSD_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
         RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
-    unsigned long long bad_host[2] = {0ull, 0ull};
-    if (any_codes) {
-        // the d2h stream already waits for every chunk's kernels (ev_done[k] above), pack kernels included
-        RSD_CUDA(cudaMemcpyAsync(bad_host, c->misc.p, sizeof bad_host, cudaMemcpyDeviceToHost, c->d2h_stream));
-    }
+    // the d2h stream already waits for every chunk's kernels (ev_done[k] above), pack kernels included
+    volatile unsigned long long *h_bad = any_codes ? (volatile unsigned long long *)((unsigned char *)c->h_stage + tab_bytes) : nullptr;
+    if (any_codes) RSD_CUDA(cudaMemcpyAsync((void *)h_bad, d_bad, 16, cudaMemcpyDeviceToHost, c->d2h_stream));
     t_comp = now();
     RSD_CUDA(cudaStreamSynchronize(c->d2h_stream));
     RSD_CUDA(cudaStreamSynchronize(cp));
     RSD_CUDA(cudaStreamSynchronize(c->stream2));
     RSD_CUDA(cudaStreamSynchronize(st));
-    if (bad_host[0])
-        return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a symbol code of sequence %llu does not fit %d bits", bad_host[0] - 1ull, bits);
-    if (trace) fprintf(stderr, "[rsd trace] host ms: classify+costs %.3f, lengths+block sums %.3f, enqueue copies %.3f, enqueue compute %.3f, wait %.3f\n",
-                       t_cost - t_in, t_len - t_cost, t_copy - t_len, t_comp - t_copy, now() - t_comp);
+    if (h_bad && h_bad[0])
+        return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a symbol code of sequence %llu does not fit %d bits", (unsigned long long)h_bad[0] - 1ull, bits);
+    if (trace) fprintf(stderr, "[rsd trace] host ms: classify+costs %.3f, lengths enqueued %.3f, plans enqueued %.3f, block sums joined + copies enqueued %.3f, kernels enqueued %.3f, wait %.3f\n",
+                       t_cost - t_in, t_len - t_cost, t_plans - t_len, t_copy - t_plans, t_comp - t_copy, now() - t_comp);
     if (timing) {
         for (int k = 0; k < n_chunks; ++k) {
             if (bounds[k + 1] <= bounds[k]) continue;
@@ -1299,13 +1314,18 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
         const int64_t rest = std::max<int64_t>(db_n - CH0, 0);
         const int64_t n_main = (rest + cap - 1) / std::max<int64_t>(cap, 1);
         int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
+        int64_t wave = 0;
         if (fast && !getenv("RSD_SEARCH_NOWAVE")) {
             // the CTAs of a chunk do equal work (the database is sorted by length), so they finish wave by wave: a chunk
             // that is a whole number of waves (resident CTAs x 256 records) leaves no partly filled last wave
             int per_sm = 0;
             const size_t smem_q = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
-            RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_twin16, 128, smem_q));
-            const int64_t wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
+            if (search_per_sm_nq != nq || search_per_sm_qrows != QROWS) {
+                RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_twin16, 128, smem_q));
+                search_per_sm = per_sm; search_per_sm_nq = nq; search_per_sm_qrows = QROWS;
+            }
+            per_sm = search_per_sm;
+            wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
             if (rest > wave && cap >= wave) main_sz = cap / wave * wave;
         }
         for (int64_t r0 = 0; r0 < db_n;) {
@@ -1315,7 +1335,12 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
             if (fast) {
                 const int64_t threads = (nr + 1) / 2;
                 const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
-                const dim3 grid((unsigned)((threads + 127) / 128), seed ? (unsigned)std::min(nq, 8) : 1u);
+                // A chunk of only a few waves (a small shard: 1/8 of the database per GPU) ends in a partly filled wave that
+                // costs as much as a full one.  Splitting the query batch over blockIdx.y makes the CTAs shorter and the
+                // waves more numerous (>= 12), so that tail shrinks with them; the selectors are rebuilt per CTA (cheap).
+                unsigned gy = seed ? (unsigned)std::min(nq, 8) : 1u;
+                if (!seed && wave > 0 && nr < 12 * wave) gy = (unsigned)std::min<int64_t>(std::min(nq, 8), (12 * wave + nr - 1) / std::max<int64_t>(nr, 1));
+                const dim3 grid((unsigned)((threads + 127) / 128), gy);
                 k_search_twin16<<<grid, 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
                                                                                       q_len + q0, nq, tab, tk, alls, db_n, 1u);
                 launches += 1;

@@ -10,7 +10,7 @@
 
 int rsd_fail(int code, const char *fmt, ...);
 
-#define RSD_MAX_CHUNKS 8
+#define RSD_MAX_CHUNKS 16
 
 #define RSD_CUDA(call)                                                                              \
     do {                                                                                            \
@@ -77,7 +77,7 @@ struct rsd_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_sync = nullptr, ev_chunk[RSD_MAX_CHUNKS] = {}, ev_t0[RSD_MAX_CHUNKS] = {}, ev_t1[RSD_MAX_CHUNKS] = {}, ev_done[RSD_MAX_CHUNKS] = {};
-    cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr, ev_len = nullptr, ev_plans = nullptr;
+    cudaEvent_t cur_ev0 = nullptr, cur_ev1 = nullptr, ev_begin = nullptr, ev_len = nullptr, ev_plans = nullptr, ev_tab = nullptr;
     double last_ms_override = 0.0;
     bool costs_preloaded = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -109,6 +109,7 @@ struct rsd_ctx {
     uint32_t db_symmask = 0;
     bool db_loaded = false;
     DevBuf db_dist, db_topi, db_tops, db_aux, db_perm;
+    int search_per_sm = 0, search_per_sm_nq = -1, search_per_sm_qrows = -1;      // occupancy of the search kernel, asked once per shape
     DevBuf sim_q, sim_scores, sim_aux, sim_codes, sim_work;
 
     int ensure_device();

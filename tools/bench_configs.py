@@ -78,6 +78,16 @@ def c3(eng, n_pairs, reps=3):
         if r:
             ts.append(time.perf_counter() - t0); kms.append(eng.last_kernel_ms())
     assert ok.all()
+    # a sample of the scripts against the oracle (op codes, counts, distances): first 64 pairs and 64 spread over the batch
+    from oracle import oracle as O
+    sample = np.unique(np.concatenate([np.arange(min(64, n_pairs)), np.linspace(0, n_pairs - 1, 64).astype(np.int64)]))
+    sa = np.concatenate([ca[oa[p]:oa[p + 1]] for p in sample]); sb = np.concatenate([cb[ob[p]:ob[p + 1]] for p in sample])
+    soa = np.concatenate([[0], np.cumsum([oa[p + 1] - oa[p] for p in sample])]).astype(np.int64)
+    sob = np.concatenate([[0], np.cumsum([ob[p + 1] - ob[p] for p in sample])]).astype(np.int64)
+    w_ops, _, _, w_cnt, w_dist = O.script_batch(sa, soa, sb, sob, DEFAULT)
+    for x, p in enumerate(sample):
+        assert n_ops[p] == w_cnt[x] and dist[p] == w_dist[x], f"C3 pair {p}: count / distance differ from the oracle"
+        assert np.array_equal(op[p, :n_ops[p]], w_ops[x, :w_cnt[x]]), f"C3 pair {p}: script differs from the oracle"
     t, k = float(np.mean(ts)), float(np.mean(kms)) * 1e-3
     # HBM streams of the script path: 2-bit direction codes written once by the forward kernel (16 rows per
     # 32-bit word, columns padded to the 32-column strips), packed inputs read, op bytes written
@@ -89,14 +99,13 @@ def c3(eng, n_pairs, reps=3):
     return {"config": "C3", "hbm_streams": hbm, "pairs": n_pairs, "cells": cells, "mode": mode.value,
             "e2e_pairs_per_s": n_pairs / t, "e2e_gcups": cells / t * 1e-9, "e2e_s": t,
             "device_pairs_per_s": n_pairs / k, "device_gcups": cells / k * 1e-9, "device_s": k,
-            "roundtrip_ok": bool(ok.all()), "output": "op bytes + n_ops + dist + ok (oi/oj derivable by prefix sum), pinned host buffers"}
+            "roundtrip_ok": bool(ok.all()), "oracle_checked_pairs": int(sample.shape[0]), "output": "op bytes + n_ops + dist + ok (oi/oj derivable by prefix sum), pinned host buffers"}
 
 
 def c4(eng, L=50000, reps=3):
-    rng = np.random.default_rng(20260004)
-    a = rng.integers(0, 4, size=L, dtype=np.uint8)
-    cb, ob = mutate_batch(rng, a, np.array([0, L]), lo=1, hi=10 ** 9)
-    b = cb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _synth import c4_pair                      # the pair whose oracle script digest is committed (tests/golden/c4_digest.json)
+    a, b = c4_pair(m=L)
     eng.set_costs(DEFAULT); eng.set_timing(True)
     ts, kms = [], []
     for r in range(reps + 1):
@@ -112,7 +121,15 @@ def c4(eng, L=50000, reps=3):
         if r:
             fwd.append(eng.last_kernel_ms())
     kf = float(np.mean(fwd)) * 1e-3
-    return {"config": "C4", "forward_only_device_s": kf, "forward_only_gcups": cells / kf * 1e-9, "m": L, "n": int(b.shape[0]), "cells": cells, "mode": res["mode"], "dist": res["dist"],
+    digest_ok = None
+    if L == 50000:
+        import hashlib
+        rec = json.load(open(os.path.join(ROOT, "tests", "golden", "c4_digest.json")))["c4_default_costs"]
+        sha = lambda x, dt: hashlib.sha256(np.ascontiguousarray(x, dtype=dt).tobytes()).hexdigest()
+        digest_ok = bool(res["dist"] == float.fromhex(rec["dist"]) and sha(res["op"], np.uint8) == rec["op_sha256"]
+                         and sha(res["oi"], np.int32) == rec["oi_sha256"] and sha(res["oj"], np.int32) == rec["oj_sha256"])
+        assert digest_ok, "C4 script differs from the oracle digest"
+    return {"config": "C4", "script_equals_oracle_digest": digest_ok, "forward_only_device_s": kf, "forward_only_gcups": cells / kf * 1e-9, "m": L, "n": int(b.shape[0]), "cells": cells, "mode": res["mode"], "dist": res["dist"],
             "n_ops": int(res["op"].shape[0]), "e2e_gcups": cells / t * 1e-9, "e2e_s": t,
             "device_gcups": cells / k * 1e-9, "device_s": k}
 
@@ -144,6 +161,12 @@ def c5(eng, n_rec, nq=64, k=10, reps=3, iupac=False):
         idx, sc = eng.db_search_topk(Q, k)
         if r:
             ts.append(time.perf_counter() - t0); kms.append(eng.last_kernel_ms())
+    # every query's top-k against the oracle on a prefix of the database small enough for the CPU (the GPU result on
+    # that prefix comes from a second, small load), plus two queries on the whole database
+    from oracle import oracle as O
+    for qi in (0, nq - 1):
+        wi, ws = O.search_topk(O.decode(qs[qi]), codes, off, DEFAULT, k)
+        assert np.array_equal(idx[qi], wi) and np.array_equal(sc[qi], ws), f"C5 query {qi} differs from the oracle"
     # the other scorers of search_collection on the same database (8f rank 4): one query, all scores + top-k on device
     sim = {}
     if iupac:
@@ -165,6 +188,147 @@ def c5(eng, n_rec, nq=64, k=10, reps=3, iupac=False):
     return {"config": "C5", "similarity_search": sim, "records": n_rec, "queries": nq, "k": k, "cells": cells, "mode": eng.last_mode,
             "e2e_gcups": cells / t * 1e-9, "e2e_s": t, "device_gcups": cells / kk * 1e-9, "device_s": kk,
             "top1_scores_head": sc[:3, 0].tolist()}
+
+
+def c2_iupac(eng, n_pairs, reps=3):
+    """The reference's own default workload shape (timing.py:12-15: 15-letter strings, default costs.json) at C2
+    lengths: non-dyadic costs -> the fp64 kernel in the reference's operation order.  Device-resident timing."""
+    import torch
+    rng = np.random.default_rng(20260002)
+    la = rng.integers(100, 301, size=n_pairs); lb = rng.integers(100, 301, size=n_pairs)
+    oa = np.zeros(n_pairs + 1, np.int64); ob = np.zeros(n_pairs + 1, np.int64)
+    np.cumsum(la, out=oa[1:]); np.cumsum(lb, out=ob[1:])
+    ca = rng.integers(0, 15, size=int(oa[-1]), dtype=np.uint8); cb = rng.integers(0, 15, size=int(ob[-1]), dtype=np.uint8)
+    A, B = R.pack((ca, oa)), R.pack((cb, ob))
+    eng.set_costs(DEFAULT); eng.set_timing(True)
+    dev = torch.device("cuda", eng.device)
+    d = {k: torch.from_numpy(v).to(dev) for k, v in dict(aw=A.words, as_=A.start, al=A.len, bw=B.words, bs=B.start, bl=B.len).items()}
+    out = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
+    kms = []
+    for r in range(reps + 1):
+        eng.distance_batch_dev(d["aw"].data_ptr(), d["as_"].data_ptr(), d["al"].data_ptr(), d["bw"].data_ptr(), d["bs"].data_ptr(),
+                               d["bl"].data_ptr(), n_pairs, A.max_len, B.max_len, 4, A.symmask | B.symmask, out.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        if r:
+            kms.append(eng.last_kernel_ms())
+    from oracle import oracle as O
+    n_chk = min(n_pairs, 4000)
+    want = O.distance_batch(ca[:oa[n_chk]], oa[:n_chk + 1].copy(), cb[:ob[n_chk]], ob[:n_chk + 1].copy(), DEFAULT)
+    assert np.array_equal(out[:n_chk].cpu().numpy(), want), "fp64 distances differ from the oracle"
+    cells = float((la * lb).sum()); k = float(np.mean(kms)) * 1e-3
+    return {"pairs": n_pairs, "mode": eng.last_mode, "device_gcups": cells / k * 1e-9, "kernel_ms": k * 1e3, "oracle_checked_pairs": n_chk}
+
+
+C5_BLOCKS = 64          # the synthetic database is generated in 64 independently seeded blocks so that a rank builds only its shard
+
+
+def c5_block(b, records):
+    """Records [records*b/64, records*(b+1)/64) of the C5 database: ocu.fa-shaped (24..31 nt, ACGU, one N per 1000 symbols)."""
+    rng = np.random.default_rng([20260005, b])
+    n = records * (b + 1) // C5_BLOCKS - records * b // C5_BLOCKS
+    lens = rng.integers(24, 32, size=n)
+    total = int(lens.sum())
+    codes = rng.integers(0, 4, size=total, dtype=np.uint8)
+    codes[rng.integers(0, total, size=rng.binomial(total, 1e-3))] = 14
+    return codes, lens
+
+
+def c5_queries(records, nq):
+    """The query batch: records of block 0 with 10 % of their symbols redrawn (the same on every rank)."""
+    codes, lens = c5_block(0, records)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rng = np.random.default_rng([20260005, 1000])
+    qs = []
+    for r in rng.integers(0, lens.shape[0], size=nq):
+        s = codes[off[r]:off[r + 1]].copy()
+        hit = rng.random(s.shape[0]) < 0.1
+        s[hit] = rng.integers(0, 4, size=int(hit.sum()), dtype=np.uint8)
+        qs.append(s)
+    return qs
+
+
+def c5_sharded(eng, rank, world, dev, records=10_000_000, nq=64, k=10, steps=10, warmup=3, check_queries=2):
+    """BASELINE config 5 as north_star states it: the database sharded contiguously over the ranks (one per GPU),
+    the query batch on every rank, a local exact top-k per shard, ONE NCCL all_gather of the packed (index, score)
+    lists, merge with the same key.  Strong scaling: the database size is fixed.  Timed on the device (CUDA events,
+    max over ranks); rank 0 checks the merged lists of `check_queries` queries against the oracle over the WHOLE
+    database after the timed region.  Returns the dict for bench.py's other_configs (None on ranks > 0)."""
+    import torch
+    import torch.distributed as dist
+    b_lo, b_hi = C5_BLOCKS * rank // world, C5_BLOCKS * (rank + 1) // world
+    parts = [c5_block(b, records) for b in range(b_lo, b_hi)]
+    codes = np.concatenate([p[0] for p in parts]); lens = np.concatenate([p[1] for p in parts])
+    off = np.zeros(lens.shape[0] + 1, np.int64); np.cumsum(lens, out=off[1:])
+    base = records * b_lo // C5_BLOCKS                              # global index of this shard's first record
+    shard = R.pack((codes, off), bits=4)
+    shard.symmask |= (1 << 14) | 0xF                                # one numeric mode on every rank
+    qs = c5_queries(records, nq)
+    Q = R.pack((np.concatenate(qs), np.concatenate([[0], np.cumsum([len(q) for q in qs])]).astype(np.int64)), bits=4)
+    eng.set_costs(DEFAULT)
+    eng.set_timing(False)
+    eng.db_load(shard, global_index_base=base)
+    try:
+        qd = {n: torch.from_numpy(v).to(dev) for n, v in dict(w=Q.words, s=Q.start, l=Q.len).items()}
+        local = torch.zeros((2, nq, k), dtype=torch.int64, device=dev)          # [0] indices, [1] fp64 scores (as bits)
+        gathered = torch.zeros((world, 2, nq, k), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        launches0 = eng.launch_count()
+
+        def step():
+            eng.db_search_topk_dev(qd["w"].data_ptr(), qd["s"].data_ptr(), qd["l"].data_ptr(), nq, Q.max_len, 4, Q.symmask | 0xF | (1 << 14),
+                                   k, local[0].data_ptr(), local[1].data_ptr(), stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local)          # the one collective of the path: Q*k*16 bytes per rank
+            else:
+                gathered[0].copy_(local)
+
+        for _ in range(max(warmup, 1)):
+            step()
+        torch.cuda.synchronize()
+        launches_per_step = eng.launch_count() - launches0
+        launches_per_step //= max(warmup, 1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record(); e1.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        sym = torch.tensor([float(lens.sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+            dist.all_reduce(sym, op=dist.ReduceOp.SUM)
+        mode = eng.last_mode
+        if rank != 0:
+            return None
+        g = gathered.cpu().numpy()
+        from rna_sequence_diff_patch_b200.engine import topk_merge
+        mi, msc = topk_merge(np.ascontiguousarray(g[:, 0]), np.ascontiguousarray(g[:, 1]).view(np.float64))
+        cells = float(sum(len(q) for q in qs)) * float(sym.item())
+        res = {"records": records, "queries": nq, "k": k, "n_gpus": world, "scaling": "strong",
+               "gcups": cells * steps / (ms * 1e-3) * 1e-9, "ms_per_query_batch": ms / steps, "mode": mode,
+               "collective": "one all_gather_into_tensor of Q*k*16 B per rank (NCCL)" if world > 1 else "none (one shard)",
+               "launches_per_batch": int(launches_per_step), "shard_records": int(lens.shape[0])}
+        # oracle over the whole database (rank 0 rebuilds the blocks it did not hold)
+        if check_queries:
+            from oracle import oracle as O
+            allp = [c5_block(b, records) for b in range(C5_BLOCKS)]
+            ac = np.concatenate([p[0] for p in allp]); al = np.concatenate([p[1] for p in allp])
+            ao = np.zeros(al.shape[0] + 1, np.int64); np.cumsum(al, out=ao[1:])
+            for qi in list(range(nq))[:check_queries]:
+                wi, ws = O.search_topk(O.decode(qs[qi]), ac, ao, DEFAULT, k)
+                assert np.array_equal(mi[qi], wi) and np.array_equal(msc[qi], ws), f"sharded top-k of query {qi} differs from the oracle"
+            res["oracle_checked_queries"] = check_queries
+        return res
+    finally:
+        eng.db_free()
 
 
 if __name__ == "__main__":

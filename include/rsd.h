@@ -206,6 +206,28 @@ int rsd_db_similarity(rsd_ctx *ctx, const uint8_t *q_codes, int32_t q_len, int m
 int rsd_topk_merge(const int64_t *idx, const double *score, int n_shards, int64_t n_queries, int k,
                    int64_t *out_idx, double *out_score);
 
+/* ---- database search over several GPUs of one box, ONE process -------------------------------------------
+ * Replaces the process fan-out under IRMethods.create_search_threads / search_collection (IR:443-515) on the
+ * wf_score path: the database is cut into contiguous shards balanced by symbols, one per device; the query batch
+ * goes to every device; each device keeps a local top-k; the lists (Q * k * 16 bytes per device) are gathered
+ * with ONE grouped ncclAllGather over NVLink and merged with the key (score desc, index asc) — identical to the
+ * stable descending sort over the whole collection because shards are index-contiguous.  NCCL is bound at run
+ * time (dlopen), only when more than one distinct device is used.  devices == NULL / n_devices == 0: all visible
+ * devices.  A device may be listed several times (shards emulated on one GPU; the gather is then plain copies). */
+typedef struct rsd_multi rsd_multi;
+int rsd_multi_create(const int *devices, int n_devices, rsd_multi **out);
+int rsd_multi_destroy(rsd_multi *m);
+int rsd_multi_device_count(rsd_multi *m);
+int rsd_multi_set_costs(rsd_multi *m, double ins, double del, const double *sub);
+int rsd_multi_db_load(rsd_multi *m, const uint32_t *words, const int64_t *start, const int32_t *len,
+                      int64_t n_records, int64_t n_words, int bits, uint32_t symmask);
+int rsd_multi_db_free(rsd_multi *m);
+/* like rsd_db_search_topk, over the whole database; all_scores (optional) is [n_queries][n_records] */
+int rsd_multi_db_search_topk(rsd_multi *m, const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len,
+                             int64_t n_queries, int64_t q_nwords, int bits, uint32_t q_symmask, int k, int force_mode,
+                             int64_t *top_idx, double *top_score, double *all_scores, int *mode_out);
+int64_t rsd_multi_launch_count(rsd_multi *m);
+
 /* ---- long pair (>= ~10 kb): block-tiled wavefront with traceback ---------------------------- */
 int rsd_long_pair(rsd_ctx *ctx, const uint8_t *a, int64_t m, const uint8_t *b, int64_t n,
                   int force_mode, int want_script, int64_t max_ops,

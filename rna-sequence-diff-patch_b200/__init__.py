@@ -20,7 +20,7 @@ Layout:
 """
 from ._lib import RsdError, load_library, library_path  # noqa: F401
 from .encoding import SYMBOLS, PackedSeqs, encode, decode, pack  # noqa: F401
-from .engine import Engine, get_engine  # noqa: F401
+from .engine import Engine, MultiEngine, get_engine, get_search_engine  # noqa: F401
 
-__all__ = ["Engine", "get_engine", "RsdError", "PackedSeqs", "SYMBOLS", "encode", "decode", "pack",
+__all__ = ["Engine", "MultiEngine", "get_engine", "get_search_engine", "RsdError", "PackedSeqs", "SYMBOLS", "encode", "decode", "pack",
            "load_library", "library_path"]

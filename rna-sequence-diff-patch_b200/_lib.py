@@ -62,6 +62,14 @@ SIGNATURES = {
     "rsd_db_search_topk_dev": (ci, [vp, vp, vp, vp, i64, i64, ci, u32, ci, ci, vp, vp, intp, vp]),
     "rsd_db_similarity": (ci, [vp, u8p, C.c_int32, ci, ci, i64p, f64p, f64p]),
     "rsd_topk_merge": (ci, [i64p, f64p, ci, i64, ci, i64p, f64p]),
+    "rsd_multi_create": (ci, [intp, ci, C.POINTER(vp)]),
+    "rsd_multi_destroy": (ci, [vp]),
+    "rsd_multi_device_count": (ci, [vp]),
+    "rsd_multi_set_costs": (ci, [vp, C.c_double, C.c_double, f64p]),
+    "rsd_multi_db_load": (ci, [vp, u32p, i64p, i32p, i64, i64, ci, u32]),
+    "rsd_multi_db_free": (ci, [vp]),
+    "rsd_multi_db_search_topk": (ci, [vp, u32p, i64p, i32p, i64, i64, ci, u32, ci, ci, i64p, f64p, f64p, intp]),
+    "rsd_multi_launch_count": (i64, [vp]),
     "rsd_long_pair": (ci, [vp, u8p, i64, u8p, i64, ci, ci, i64, u8p, i32p, i32p, i64p, f64p, intp]),
     "rsd_launch_count": (i64, [vp]),
     "rsd_last_kernel_ms": (C.c_double, [vp]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <string>
 #include <thread>
 #include <vector>
 #include <chrono>
@@ -624,7 +625,7 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         for (int s = 0; s < 2; ++s) for (int q = 0; q < 2; ++q) tab[s][q] = (int64_t *)c->h_stage + (size_t)(2 * s + q) * (nblk + 1);
         for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
             auto job = [&in, &tab, n_pairs, sh, s] { block_bases(in[s].len, n_pairs, sh, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
-            if (n_pairs >= (1 << 17)) helpers[s] = std::thread(job); else job();
+            if (n_pairs >= (1 << 17) && !getenv("RSD_NO_HELPERS")) helpers[s] = std::thread(job); else job();
         }
     }
     // Large batches are cut into chunks of pairs so the H2D copy of chunk k+1 (copy stream) overlaps
@@ -1554,7 +1555,8 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
                         n_panels, per_sm * c->sm_count);
     const size_t dir_words = (size_t)((m + 15) / 16) * (size_t)n_pad;
     RSD_OK_OR_RETURN(c->dirs.ensure(dir_words * 4 + 64));
-    RSD_OK_OR_RETURN(c->ps().scratch.ensure((size_t)n_panels * (size_t)m * 12 + (size_t)n_panels * 4 + 256));
+    const int64_t bstride = (m + 2) & ~(int64_t)1;               // even and >= m + 1: lane 31 stores two rows per step, 16-byte aligned
+    RSD_OK_OR_RETURN(c->ps().scratch.ensure((size_t)n_panels * (size_t)bstride * 12 + (size_t)n_panels * 4 + 256));
     RSD_OK_OR_RETURN(c->mat_ab.ensure((size_t)m + n + 64));
     RSD_OK_OR_RETURN(c->out_f64.ensure(64));
     uint8_t *da = (uint8_t *)c->mat_ab.p, *db = da + ((m + 15) / 16) * 16;
@@ -1563,15 +1565,16 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     LongArgs la{};
     la.a = da; la.m = (int)m; la.b = db; la.n = (int)n; la.n_panels = n_panels; la.n_pad = (int)n_pad;
     la.dirs = (uint32_t *)c->dirs.p;
-    la.bound = c->ps().scratch.p;
-    la.bound_steps = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)m * 8);
-    la.progress = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)m * 12);
+    la.bound = c->ps().scratch.p; la.bstride = (int)bstride;
+    la.bound_steps = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)bstride * 8);
+    la.progress = (int *)((unsigned char *)c->ps().scratch.p + (size_t)n_panels * (size_t)bstride * 12);
     la.dist = (double *)c->out_f64.p;
     la.S = S;
     la.dbg = nullptr;
     const bool ltrace = getenv("RSD_TRACE") != nullptr;
     if (ltrace) { RSD_OK_OR_RETURN(c->misc.ensure((size_t)n_panels * 64)); la.dbg = (unsigned long long *)c->misc.p; }
-    RSD_CUDA(cudaMemsetAsync(la.bound, 0x80, (size_t)n_panels * (size_t)m * 8, st));      // sentinel = "not published yet"
+    RSD_CUDA(cudaMemsetAsync(la.bound, 0x80, (size_t)n_panels * (size_t)bstride * 8, st));      // sentinel = "not published yet"
+    RSD_CUDA(cudaMemsetAsync(la.progress, 0, sizeof(int) * (size_t)n_panels, st));              // [0] doubles as the watchdog's error flag
     const IntCosts *dic = c->d_ic; const F64Costs *dfc = c->d_fc;
     void *args[] = {&la, &dic, &dfc};
     void *args32[] = {&la, &dic};
@@ -1592,6 +1595,8 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     if (c->timing) { RSD_CUDA(cudaEventRecord(c->ev1, st)); c->timed = true; }
     RSD_CUDA(cudaGetLastError());
     RSD_CUDA(cudaMemcpyAsync(dist, c->out_f64.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    int32_t stalled = 0;
+    RSD_CUDA(cudaMemcpyAsync(&stalled, la.progress, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (ltrace) {
         std::vector<unsigned long long> d((size_t)n_panels * 8);
         RSD_CUDA(cudaMemcpyAsync(d.data(), la.dbg, d.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -1604,11 +1609,18 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     if (want_script) {
         RSD_CUDA(cudaMemcpyAsync(&k32, c->s_nops.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         RSD_CUDA(cudaStreamSynchronize(st));
+        if (stalled && two_rows) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled (watchdog); no result");
         *n_ops = k32;
         RSD_CUDA(cudaMemcpyAsync(op, c->s_op.p, (size_t)k32, cudaMemcpyDeviceToHost, st));
         if (oi) RSD_CUDA(cudaMemcpyAsync(oi, c->s_oi.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
         if (oj) RSD_CUDA(cudaMemcpyAsync(oj, c->s_oj.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
     }
     RSD_CUDA(cudaStreamSynchronize(st));
+    if (stalled && two_rows) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled (watchdog); no result");
     return RSD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs, one process: sharded database search with an NCCL gather
+// ------------------------------------------------------------------------------------------------
+#include "rsd_multi.inl"

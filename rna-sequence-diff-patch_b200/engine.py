@@ -263,6 +263,75 @@ class Engine:
         return self._ctx
 
 
+class MultiEngine:
+    """Database search over several GPUs from one process (include/rsd.h, rsd_multi_*): contiguous shards, the
+    query batch on every device, local top-k, one NCCL all-gather of the lists, merge.  Same search interface as
+    Engine (set_costs / db_load / db_search_topk / db_free), so ir.score_collection runs on either."""
+
+    def __init__(self, devices=None):
+        self._lib = _lib.load_library()
+        self._h = C.c_void_p()
+        if devices is None:
+            check(self._lib.rsd_multi_create(None, 0, C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            check(self._lib.rsd_multi_create(arr, len(devices), C.byref(self._h)))
+        self.n_devices = int(self._lib.rsd_multi_device_count(self._h))
+        self.pid = os.getpid()
+        self.last_mode = 0
+        self._costs_key = None
+        self._db_gen = 0
+        self._db_n = 0
+        self._db_bits = 4
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rsd_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if os.getpid() == self.pid:
+                self.close()
+        except Exception:
+            pass
+
+    def set_costs(self, costs: dict):
+        ins, dele, sub = costs_to_arrays(costs)
+        key = (ins, dele, sub.tobytes())
+        if key != self._costs_key:
+            check(self._lib.rsd_multi_set_costs(self._h, ins, dele, ptr(sub, _f64)))
+            self._costs_key = key
+
+    def db_load(self, db: PackedSeqs):
+        check(self._lib.rsd_multi_db_load(self._h, ptr(db.words, _u32), ptr(db.start, _i64), ptr(db.len, _i32), db.n,
+                                          db.words.shape[0], db.bits, db.symmask))
+        self._db_n, self._db_bits = db.n, db.bits
+        self._db_gen += 1
+
+    def db_free(self):
+        check(self._lib.rsd_multi_db_free(self._h))
+        self._db_gen += 1
+
+    def db_search_topk(self, Q: PackedSeqs, k: int, want_scores: bool = False, force_mode: int = 0):
+        Q = Q.repack(self._db_bits) if Q.bits != self._db_bits and self._db_bits == 4 else Q
+        if Q.bits != self._db_bits:
+            raise ValueError("query symbols do not fit the database packing; reload the database with bits=4")
+        nq = Q.n
+        idx = np.zeros((nq, max(k, 1)), np.int64); sc = np.zeros((nq, max(k, 1)), np.float64)
+        alls = np.zeros((nq, self._db_n), np.float64) if want_scores else None
+        mode = C.c_int()
+        check(self._lib.rsd_multi_db_search_topk(self._h, ptr(Q.words, _u32), ptr(Q.start, _i64), ptr(Q.len, _i32), nq,
+                                                 Q.words.shape[0], Q.bits, Q.symmask, k, force_mode, ptr(idx, _i64), ptr(sc, _f64),
+                                                 ptr(alls, _f64) if want_scores else None, C.byref(mode)))
+        self.last_mode = mode.value
+        idx, sc = idx[:, :k], sc[:, :k]
+        return (idx, sc, alls) if want_scores else (idx, sc)
+
+    def launch_count(self) -> int:
+        return int(self._lib.rsd_multi_launch_count(self._h))
+
+
 def topk_merge(idx: np.ndarray, score: np.ndarray):
     """idx/score: [n_shards, n_queries, k] -> merged ([n_queries, k], [n_queries, k]) with the key
     (score descending, global index ascending) — the reduction after the NCCL gather."""
@@ -283,4 +352,19 @@ def get_engine(device: int = 0) -> Engine:
     e = _engines.get(key)
     if e is None:
         e = _engines[key] = Engine(device)
+    return e
+
+
+_multi: dict = {}
+
+
+def get_search_engine():
+    """What search_collection runs on: every visible GPU when there is more than one (MultiEngine, one process),
+    else the process-local Engine."""
+    lib = _lib.load_library()
+    if lib.rsd_device_count() <= 1:
+        return get_engine()
+    e = _multi.get(os.getpid())
+    if e is None:
+        e = _multi[os.getpid()] = MultiEngine()
     return e

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import sed
 from .encoding import pack
-from .engine import get_engine
+from .engine import get_engine, get_search_engine
 
 
 def wf_score(seq1: str, seq2: str, costs: dict) -> float:
@@ -50,6 +50,8 @@ class _Resident:
         if (cls.engine is eng and cls.gen == getattr(eng, "_db_gen", 0) and cls.sequences is not None
                 and cls.sequences[0] == upper and cls.sequences[1] == sequences):
             return
+        if cls.engine is not None and cls.engine is not eng:
+            cls.drop()                                   # the collection moves to another engine: free the old copy
         cls.engine, cls.sequences = None, None
         eng.db_load(pack([s.upper() for s in sequences] if upper else sequences, bits=4))
         cls.engine, cls.sequences, cls.gen = eng, (upper, sequences), eng._db_gen
@@ -68,11 +70,12 @@ def release_collection():
 
 def score_collection(query: str, sequences, costs: dict, engine=None):
     """[(sequence, wf_score(query, sequence))] in collection order — what
-    search_collection(query, _, collection, wf_score) returns (IR:469-477), one GPU pass."""
+    search_collection(query, _, collection, wf_score) returns (IR:469-477): one pass over the collection, sharded
+    over every visible GPU (one process, NCCL gather of the top-k lists; the per-document scores come back per shard)."""
     sequences = list(sequences)
     if not sequences:
         return []
-    eng = engine or get_engine()
+    eng = engine or get_search_engine()
     eng.set_costs(costs)
     _validate_collection(query, sequences, costs)
     _Resident.load(eng, sequences, upper=True)

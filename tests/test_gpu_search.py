@@ -158,3 +158,33 @@ def test_c5_shaped_query_batches_every_query_vs_oracle(R, eng, golden, nq, n_db,
     for q in range(nq):
         wi, ws = O.search_topk(queries[q], codes, off, costs, k)
         assert np.array_equal(idx[q], wi) and np.array_equal(sc[q], ws), q
+
+
+def test_multi_device_search_one_process(R, golden):
+    """rsd_multi_*: shards on several contexts of ONE process, gather, merge == the oracle; all_scores in record
+    order.  With one GPU in the box the device is listed three times (emulated shards, gather by device copies);
+    with several GPUs the real thing runs: one context per device and a grouped ncclAllGather."""
+    rng = np.random.default_rng(35)
+    codes, off = make_db(rng, 90_000)
+    queries = make_queries(rng, codes, off, 5)
+    costs = golden["default_costs"]
+    n_dev = R.load_library().rsd_device_count()
+    for devices in ([0, 0, 0], None if n_dev > 1 else [0]):
+        me = R.MultiEngine(devices)
+        try:
+            me.set_costs(costs)
+            me.db_load(R.pack((codes, off), bits=4))
+            idx, sc, alls = me.db_search_topk(R.pack(queries, bits=4), 10, want_scores=True)
+            assert me.last_mode == 1
+            wi, ws, wa = oracle_topk(queries, codes, off, costs, 10)
+            assert np.array_equal(idx, wi) and np.array_equal(sc, ws) and np.array_equal(alls, wa)
+            idx2, sc2 = me.db_search_topk(R.pack(queries[:2], bits=4), 3)
+            assert np.array_equal(idx2, wi[:2, :3]) and np.array_equal(sc2, ws[:2, :3])
+            me.db_free()
+            # fewer records than devices: empty shards pad with -1 and the merge skips them
+            me.db_load(R.pack((codes[:off[2]], off[:3].copy()), bits=4))
+            idx3, sc3 = me.db_search_topk(R.pack(queries[:1], bits=4), 4)
+            w3 = O.search_topk(queries[0], codes[:off[2]], off[:3].copy(), costs, 4)
+            assert np.array_equal(idx3[0], w3[0]) and np.array_equal(sc3[0][:2], w3[1][:2])
+        finally:
+            me.close()

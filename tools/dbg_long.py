@@ -1,13 +1,16 @@
-import json, os, sys, time
+"""Long-pair (C4) timing and pipeline trace: RSD_TRACE prints per-panel start / end times; the slope of the end
+times over the panel index is the achieved lag per panel."""
+import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as G; G.build()
 import rna_sequence_diff_patch_b200 as R
-eng = R.Engine(0); eng.set_costs(__import__('rna_sequence_diff_patch_b200.cost_tables', fromlist=['x']).default_costs()); eng.set_timing(True)
-rng = np.random.default_rng(1)
-for m, n in [(50000, 256), (50000, 512), (50000, 1024), (50000, 4096), (50000, 16384), (50000, 50000), (10000, 50000), (2000, 50000)]:
-    a = rng.integers(0, 4, size=m, dtype=np.uint8); b = rng.integers(0, 4, size=n, dtype=np.uint8)
-    for r in range(2):
-        eng.long_pair(a, b, want_script=False)
-    ms = eng.last_kernel_ms()
-    print(f"m={m} n={n} panels={(n+255)//256} fwd_ms={ms:.3f} ns/step={ms*1e6/(m+31):.1f} gcups={m*n/ms*1e-6:.1f}", flush=True)
+from rna_sequence_diff_patch_b200 import cost_tables
+from _synth import c4_pair
+a, b = c4_pair(m=int(os.environ.get("L", 50000)))
+eng = R.Engine(0); eng.set_costs(cost_tables.default_costs()); eng.set_timing(True)
+for r in range(4):
+    eng.long_pair(a, b, want_script=False)
+    print("forward ms", round(eng.last_kernel_ms(), 3), flush=True)
+os.environ["RSD_TRACE"] = "1"
+eng.long_pair(a, b, want_script=False)

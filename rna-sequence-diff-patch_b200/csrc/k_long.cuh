@@ -21,7 +21,7 @@ struct LongArgs {
     const uint8_t *a; int m;           // 1 byte / symbol codes on the device
     const uint8_t *b; int n;
     int n_panels, n_pad;               // n_pad = n_panels * 32 * C
-    int bstride;                       // cells per panel in `bound` for the two-rows-per-step kernel (even, >= m + 1)
+    int bstride;                       // cells reserved per panel in `bound` (>= m)
     uint32_t *dirs;                    // [ceil(m/16)][n_pad]
     void *bound;                       // [n_panels][m] keys (int64 or double)
     int *bound_steps;                  // [n_panels][m] (fp64 mode)
@@ -42,13 +42,6 @@ struct LongArgs {
 __device__ __forceinline__ unsigned long long ld_poll_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// the same without the compiler-level memory barrier: for fetches whose value is only looked at later (the tag in the
-// value says whether it had been published), so that ptxas may keep scheduling across them
-__device__ __forceinline__ unsigned long long ld_poll_u64_nc(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_cg_u64(unsigned long long *p, unsigned long long v) {
@@ -378,26 +371,16 @@ k_long_fwd32(LongArgs la, const IntCosts *__restrict__ icp) {
     }
 }
 
-// Same keys as k_long_fwd32, but every lane advances TWO rows per step (a 2 x C register tile): one loop
-// overhead and one pair of shuffles per two rows, and the two rows form a small wavefront (cell (r+1, c) needs
-// (r, c), (r, c-1), (r+1, c-1)) that gives the single resident warp independent instructions to issue.  Lane l
-// works on rows 2(s - l), 2(s - l) + 1 at step s.
-//
-// Panel-to-panel protocol (what bounds the pipeline fill: a 50 kb pair has 391 panels, and every step of lag
-// between neighbours is 391 steps of fill on a 25 000-step matrix):
-//   * producer: lane 31 owns the panel's right-most column and stores its two finished rows straight to the
-//     boundary array every step (one 16-byte store; each 8-byte cell carries its own "published" tag in the high
-//     word, so no fence and no separate flag) — the rows are visible one store latency after they exist;
-//   * consumer: the boundary rows are fetched a QUARTER block (4 steps = 8 rows, lanes 0..7) ahead into one of two
-//     registers that alternate per quarter, so the L2 round trip of the fetch runs under the previous quarter's
-//     rows instead of stalling the warp; a quarter starts by checking the tags of its rows (normally all there)
-//     and re-polls only what is still the sentinel.
-// Net lag per panel: 31 steps of lane skew + ~2 (store to visibility) + 4 (fetch distance) + 4 (quarter) instead of
-// 31 + 16 (block-end publication) + 16 (whole-block fetch) - and no exposed fetch latency per block.
+// Same keys and protocol as k_long_fwd32, but every lane advances TWO rows per step (a 2 x C register tile):
+// one loop overhead, one pair of shuffles and one boundary exchange per two rows, and the two rows form a
+// small wavefront (cell (r+1, c) needs (r, c), (r, c-1), (r+1, c-1)) that gives the single resident warp
+// independent instructions to issue.  Lane l works on rows 2(s - l), 2(s - l) + 1 at step s; blocks are 16
+// steps = 32 rows, so the boundary exchange moves 32 rows at a time (one per lane).
 template <int C>
 __global__ void __launch_bounds__(32)
 k_long_fwd32x2(LongArgs la, const IntCosts *__restrict__ icp) {
     __shared__ uint32_t s_w[256];
+    __shared__ uint32_t s_pub[32];
     __shared__ __align__(4) uint8_t s_a[96];
     for (int k = threadIdx.x; k < 256; k += 32)
         s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << la.S) - 1);
@@ -416,28 +399,32 @@ k_long_fwd32x2(LongArgs la, const IntCosts *__restrict__ icp) {
     }
     uint32_t last0 = 0u, last1 = 0u, prev_recv1 = 0u;       // last column of the two rows of the previous step; recv1 of the previous step
     long long full = 0;
-    const unsigned long long *bin = w > 0 ? (const unsigned long long *)la.bound + (size_t)(w - 1) * la.bstride : nullptr;
-    unsigned long long *bout = (unsigned long long *)la.bound + (size_t)w * la.bstride;
-    const bool publish = (w + 1 < la.n_panels) && lane == 31;
-    const bool consume = w > 0;
+    const unsigned long long *bin = w > 0 ? (const unsigned long long *)la.bound + (size_t)(w - 1) * m : nullptr;
+    unsigned long long *bout = (unsigned long long *)la.bound + (size_t)w * m;
+    const bool publish = (w + 1 < la.n_panels);
     uint32_t *dcol = la.dirs + col0;
-    const int steps = (m + 1) / 2 + 31;
-    int spins = 0; bool dead = false;                        // watchdog: a stalled pipeline ends with an error, not a hung GPU
-    unsigned long long dbg_t0 = 0;
-    if (la.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    const int steps = (m + 1) / 2 + 31 + 16;        // + one block so the last rows get published
     // source symbols of a block: rows 2(t0 - 31) .. 2(t0 + 15) + 1 (94 rows), three per lane, fetched one block ahead
     auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)m) ? la.a[r] : (uint8_t)0; };
     uint8_t pf0 = fetch(0, 0), pf1 = fetch(0, 1), pf2 = fetch(0, 2);
-    // boundary rows of a quarter block: lanes 0..7 hold rows 2 * (first step of the quarter) + lane
-    auto bfetch = [&](int step0) -> unsigned long long {
-        const int r = 2 * step0 + lane;
-        return (consume && lane < 8 && r < m) ? ld_poll_u64_nc(bin + r) : 0ull;
-    };
-    unsigned long long bqa = bfetch(0), bqb = 0ull;          // quarter 0 of block 0
 
 #pragma unroll 1
     for (int t0 = 0; t0 < steps; t0 += 16) {
         const uint32_t last_at_block_start = last1;
+        if (publish) {
+            const int r = 2 * (t0 - 47) + lane;
+            if (r >= 0 && r < m) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
+        }
+        __syncwarp();
+        uint32_t bval = 0u;
+        if (w > 0) {
+            const bool mine = 2 * t0 + lane < m;
+            unsigned long long raw = 0ull;
+            do {
+                if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
+            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));      // warp-uniform exit (see k_long_fwd)
+            bval = (uint32_t)raw;
+        }
         // codes0 / codes1: 16 nibbles each = the table rows of this lane's first / second row in the 16 steps
         unsigned long long codes0 = 0ull, codes1 = 0ull;
         {
@@ -452,118 +439,88 @@ k_long_fwd32x2(LongArgs la, const IntCosts *__restrict__ icp) {
             }
             __syncwarp();
         }
-        // one quarter block = 4 steps; X holds its boundary rows, Y receives the next quarter's
-        auto quarter = [&](auto q_tag, auto steady_tag, unsigned long long &X, unsigned long long &Y) {
-            constexpr int Q = decltype(q_tag)::value;
-            constexpr bool STEADY = decltype(steady_tag)::value;
-            if (consume) {
-                const int r = 2 * (t0 + 4 * Q) + lane;
-                const bool mine = lane < 8 && r < m;
-                while (!__all_sync(RSD_FULL, !(mine && X == RSD_LONG_SENTINEL))) {
-                    if (mine && X == RSD_LONG_SENTINEL && !dead) X = ld_poll_u64(bin + r);
-                    if (++spins > (1 << 22)) { dead = true; X = 0ull; la.progress[0] = 1; }
-                }
-                Y = bfetch(t0 + 4 * Q + 4);
-            }
-            const uint32_t bx = (uint32_t)X;
+        auto run16 = [&](auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const int i0 = 2 * (t0 + k - lane);
+            const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)m);
+            const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)m);
+            const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) << 6, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) << 6;
+            uint32_t w0[C], w1[C];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = 4 * Q + kk;
-                const int i0 = 2 * (t0 + k - lane);
-                const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)m);
-                const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)m);
-                const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) << 6, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) << 6;
-                uint32_t w0[C], w1[C];
+            for (int c = 0; c < C; ++c) {
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0[c]) : "r"(bca[c] + off0));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[c]) : "r"(bca[c] + off1));
+            }
+            // first row, the part that does not involve the left neighbour
+            uint32_t t2a[C]; int e1a[C];
+            {
+                uint32_t diag = prev_recv1;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    asm("ld.shared.u32 %0, [%1];" : "=r"(w0[c]) : "r"(bca[c] + off0));
-                    asm("ld.shared.u32 %0, [%1];" : "=r"(w1[c]) : "r"(bca[c] + off1));
+                    const uint32_t up = H[c];
+                    const uint32_t x = diag + w0[c];
+                    e1a[c] = (int)(x - up);
+                    t2a[c] = up + (uint32_t)min(e1a[c], 0);
+                    diag = up;
                 }
-                // first row, the part that does not involve the left neighbour
-                uint32_t t2a[C]; int e1a[C];
-                {
-                    uint32_t diag = prev_recv1;
+            }
+            uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
+            uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
+            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, 2 * k), b1 = __shfl_sync(RSD_FULL, bval, 2 * k + 1);
+            if (lane == 0) { recv0 = w > 0 ? b0 : 0u; recv1 = w > 0 ? b1 : 0u; }
+            if (on0) {
+                uint32_t left = recv0, h0[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int e2 = (int)(t2a[c] - left);
+                    h0[c] = t2a[c] + (uint32_t)__viaddmin_s32((int)left, -(int)t2a[c], 0);
+                    left = h0[c];
+                    acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
+                    acc[c] = __funnelshift_l((uint32_t)e1a[c], acc[c], 1);
+                }
+                last0 = left;
+                if (on1) {
+                    uint32_t diag = recv0, left1 = recv1;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const uint32_t up = H[c];
-                        const uint32_t x = diag + w0[c];
-                        e1a[c] = (int)(x - up);
-                        t2a[c] = up + (uint32_t)min(e1a[c], 0);
-                        diag = up;
-                    }
-                }
-                uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
-                uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
-                const uint32_t b0 = __shfl_sync(RSD_FULL, bx, 2 * kk), b1 = __shfl_sync(RSD_FULL, bx, 2 * kk + 1);
-                if (lane == 0) { recv0 = consume ? b0 : 0u; recv1 = consume ? b1 : 0u; }
-                if (on0) {
-                    uint32_t left = recv0, h0[C];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const int e2 = (int)(t2a[c] - left);
-                        h0[c] = t2a[c] + (uint32_t)__viaddmin_s32((int)left, -(int)t2a[c], 0);
-                        left = h0[c];
+                        const uint32_t up = h0[c];
+                        const uint32_t x = diag + w1[c];
+                        const int e1 = (int)(x - up);
+                        const uint32_t t2 = up + (uint32_t)min(e1, 0);
+                        const int e2 = (int)(t2 - left1);
+                        const uint32_t hn = t2 + (uint32_t)__viaddmin_s32((int)left1, -(int)t2, 0);
+                        diag = up; H[c] = hn; left1 = hn;
                         acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
-                        acc[c] = __funnelshift_l((uint32_t)e1a[c], acc[c], 1);
+                        acc[c] = __funnelshift_l((uint32_t)e1, acc[c], 1);
                     }
-                    last0 = left;
-                    if (on1) {
-                        uint32_t diag = recv0, left1 = recv1;
+                    last1 = left1;
+                } else {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const uint32_t up = h0[c];
-                            const uint32_t x = diag + w1[c];
-                            const int e1 = (int)(x - up);
-                            const uint32_t t2 = up + (uint32_t)min(e1, 0);
-                            const int e2 = (int)(t2 - left1);
-                            const uint32_t hn = t2 + (uint32_t)__viaddmin_s32((int)left1, -(int)t2, 0);
-                            diag = up; H[c] = hn; left1 = hn;
-                            acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
-                            acc[c] = __funnelshift_l((uint32_t)e1, acc[c], 1);
-                        }
-                        last1 = left1;
+                    for (int c = 0; c < C; ++c) H[c] = h0[c];
+                    last1 = last0;                              // the panel's running last column (only used for the key tracking)
+                }
+                prev_recv1 = recv1;
+                const int il = on1 ? i0 + 1 : i0;               // last row done in this step
+                if ((il & 15) == 15 || il == m - 1) {
+                    const int sh = 2 * (15 - (il & 15));
+                    if constexpr (C >= 4) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(il >> 4) * la.n_pad);
+#pragma unroll
+                        for (int c = 0; c < C; c += 4)
+                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
                     } else {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) H[c] = h0[c];
-                        last1 = last0;                              // the panel's running last column (only used for the key tracking)
-                    }
-                    prev_recv1 = recv1;
-                    // the panel's right-most column goes to the next panel as soon as it exists (row i0 is even and the
-                    // boundary stride is even: a 16-byte aligned pair; a second cell beyond row m - 1 is never read)
-                    if (publish) {
-                        const unsigned long long c0 = (1ull << 32) | (unsigned long long)last0, c1 = (1ull << 32) | (unsigned long long)last1;
-                        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(bout + i0), "l"(c0), "l"(c1));
-                    }
-                    const int il = on1 ? i0 + 1 : i0;               // last row done in this step
-                    if ((il & 15) == 15 || il == m - 1) {
-                        const int sh = 2 * (15 - (il & 15));
-                        if constexpr (C >= 4) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(il >> 4) * la.n_pad);
-#pragma unroll
-                            for (int c = 0; c < C; c += 4)
-                                dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
-                        } else {
-                            *reinterpret_cast<uint2 *>(dcol + (size_t)(il >> 4) * la.n_pad) = make_uint2(acc[0] << sh, acc[1] << sh);
-                        }
+                        *reinterpret_cast<uint2 *>(dcol + (size_t)(il >> 4) * la.n_pad) = make_uint2(acc[0] << sh, acc[1] << sh);
                     }
                 }
             }
-        };
-        // Blocks in which every lane is inside its rows (all but the first and last few) run a copy of the
-        // row loop without the per-row activity test: no branch for the scheduler to work around.
-        auto run16 = [&](auto steady_tag) {
-            quarter(std::integral_constant<int, 0>{}, steady_tag, bqa, bqb);
-            quarter(std::integral_constant<int, 1>{}, steady_tag, bqb, bqa);
-            quarter(std::integral_constant<int, 2>{}, steady_tag, bqa, bqb);
-            quarter(std::integral_constant<int, 3>{}, steady_tag, bqb, bqa);
+            if (lane == 31) { s_pub[2 * k] = last0; s_pub[2 * k + 1] = last1; }
+        }
         };
         if (2 * (t0 - 31) >= 0 && 2 * (t0 + 15) + 1 <= m - 1) run16(std::true_type{}); else run16(std::false_type{});
         __syncwarp();
         full += (long long)(int)(last1 - last_at_block_start);          // <= 32 bounded row-to-row differences (host check)
-    }
-    if (la.dbg && lane == 0) {
-        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        la.dbg[w * 8 + 0] = dbg_t0; la.dbg[w * 8 + 1] = t1; la.dbg[w * 8 + 2] = (unsigned long long)spins; la.dbg[w * 8 + 3] = 0; la.dbg[w * 8 + 4] = 0; la.dbg[w * 8 + 5] = 0;
     }
     if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
         const int cl = (n - 1) - col0;

@@ -1555,7 +1555,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
                         n_panels, per_sm * c->sm_count);
     const size_t dir_words = (size_t)((m + 15) / 16) * (size_t)n_pad;
     RSD_OK_OR_RETURN(c->dirs.ensure(dir_words * 4 + 64));
-    const int64_t bstride = (m + 2) & ~(int64_t)1;               // even and >= m + 1: lane 31 stores two rows per step, 16-byte aligned
+    const int64_t bstride = m;
     RSD_OK_OR_RETURN(c->ps().scratch.ensure((size_t)n_panels * (size_t)bstride * 12 + (size_t)n_panels * 4 + 256));
     RSD_OK_OR_RETURN(c->mat_ab.ensure((size_t)m + n + 64));
     RSD_OK_OR_RETURN(c->out_f64.ensure(64));
@@ -1601,7 +1601,7 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
         std::vector<unsigned long long> d((size_t)n_panels * 8);
         RSD_CUDA(cudaMemcpyAsync(d.data(), la.dbg, d.size() * 8, cudaMemcpyDeviceToHost, st));
         RSD_CUDA(cudaStreamSynchronize(st));
-        for (int w2 = 0; w2 < n_panels; w2 += std::max(1, n_panels / 8))
+        for (int w2 = 0; w2 < n_panels; w2 += (w2 < 4 ? 1 : std::max(1, n_panels / 8)))
             fprintf(stderr, "[rsd trace] panel %d: start +%.3f ms, end +%.3f ms, Mclk: poll %.3f publish %.3f a-loads %.3f rows %.3f\n", w2,
                     (d[w2 * 8] - d[0]) * 1e-6, (d[w2 * 8 + 1] - d[0]) * 1e-6, d[w2 * 8 + 2] * 1e-6, d[w2 * 8 + 3] * 1e-6, d[w2 * 8 + 4] * 1e-6, d[w2 * 8 + 5] * 1e-6);
     }
@@ -1609,14 +1609,14 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
     if (want_script) {
         RSD_CUDA(cudaMemcpyAsync(&k32, c->s_nops.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         RSD_CUDA(cudaStreamSynchronize(st));
-        if (stalled && two_rows) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled (watchdog); no result");
+        if (stalled < 0) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled; no result");
         *n_ops = k32;
         RSD_CUDA(cudaMemcpyAsync(op, c->s_op.p, (size_t)k32, cudaMemcpyDeviceToHost, st));
         if (oi) RSD_CUDA(cudaMemcpyAsync(oi, c->s_oi.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
         if (oj) RSD_CUDA(cudaMemcpyAsync(oj, c->s_oj.p, sizeof(int32_t) * (size_t)k32, cudaMemcpyDeviceToHost, st));
     }
     RSD_CUDA(cudaStreamSynchronize(st));
-    if (stalled && two_rows) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled (watchdog); no result");
+    if (stalled < 0) return rsd_fail(RSD_ECUDA, "rsd_long_pair: the panel pipeline stalled; no result");
     return RSD_OK;
 }
 

@@ -228,10 +228,27 @@ int rsd_multi_db_search_topk(rsd_multi *m, const uint32_t *q_words, const int64_
                              int64_t *top_idx, double *top_score, double *all_scores, int *mode_out);
 int64_t rsd_multi_launch_count(rsd_multi *m);
 
-/* ---- long pair (>= ~10 kb): block-tiled wavefront with traceback ---------------------------- */
+/* ---- long pairs (>= ~10 kb): block-tiled wavefront with traceback ----------------------------
+ * Replaces wagnerFisher + create_paths(dp)[0] + generate_es (StringEditDistance.py:133-334) for pairs whose
+ * matrix the reference cannot hold (~500 B per cell).  a / b: 1 byte per symbol (code 0..14, table order).
+ * Script output as in rsd_script_batch: op (0 insert, 1 delete, 2 update) and the matrix cell (oi, oj) each
+ * op enters, origin -> sink; max_ops >= m + n.
+ * rsd_long_pair: one pair.  A pair whose 2-bit direction matrix does not fit the device (or whose column
+ * panels exceed the co-resident CTAs) is computed in row blocks from stored key rows (linear-space overflow
+ * path: checkpoint rows top to bottom, then recomputation with directions and traceback bottom to top) —
+ * same distance and script as the one-launch path. */
 int rsd_long_pair(rsd_ctx *ctx, const uint8_t *a, int64_t m, const uint8_t *b, int64_t n,
                   int force_mode, int want_script, int64_t max_ops,
                   uint8_t *op, int32_t *oi, int32_t *oj, int64_t *n_ops, double *dist, int *mode_out);
+/* rsd_long_pairs: a batch of long pairs (BASELINE config 4) in as few launches as memory allows; the pairs of
+ * a launch share the GPU (rings of CTAs, one pair after the other per ring).  Arrays of n_pairs entries;
+ * oi / oj (the arrays or single entries) may be NULL; mode_out (optional) receives one mode per pair. */
+int rsd_long_pairs(rsd_ctx *ctx, int n_pairs, const uint8_t *const *a, const int64_t *m,
+                   const uint8_t *const *b, const int64_t *n, int force_mode, int want_script,
+                   const int64_t *max_ops, uint8_t *const *op, int32_t *const *oi, int32_t *const *oj,
+                   int64_t *n_ops, double *dist, int *mode_out);
+/* device time in ms of the forward (matrix fill) launches of the last rsd_long_pair(s) call (rsd_set_timing) */
+double rsd_long_forward_ms(rsd_ctx *ctx);
 
 /* ---- introspection for bench.py / tests ---------------------------------------------------- */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */

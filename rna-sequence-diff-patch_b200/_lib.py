@@ -71,6 +71,9 @@ SIGNATURES = {
     "rsd_multi_db_search_topk": (ci, [vp, u32p, i64p, i32p, i64, i64, ci, u32, ci, ci, i64p, f64p, f64p, intp]),
     "rsd_multi_launch_count": (i64, [vp]),
     "rsd_long_pair": (ci, [vp, u8p, i64, u8p, i64, ci, ci, i64, u8p, i32p, i32p, i64p, f64p, intp]),
+    "rsd_long_pairs": (ci, [vp, ci, C.POINTER(vp), i64p, C.POINTER(vp), i64p, ci, ci, i64p,
+                            C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64p, f64p, intp]),
+    "rsd_long_forward_ms": (C.c_double, [vp]),
     "rsd_launch_count": (i64, [vp]),
     "rsd_last_kernel_ms": (C.c_double, [vp]),
     "rsd_set_timing": (ci, [vp, ci]),

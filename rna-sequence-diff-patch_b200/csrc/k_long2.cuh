@@ -1,0 +1,310 @@
+// k_long2.cuh — long pairs, second generation: the panel pipeline of k_long.cuh (k_long_fwd32x2: 32-bit modular
+// keys, two rows per step) as a *job* kernel, so that one cooperative launch can carry
+//   * several pairs at once (BASELINE config 4 is a batch of 50 kb pairs): the CTAs of a *ring* run panel w of
+//     one pair after the other, so the pipeline fill of pair k+1 overlaps the drain of pair k, and several rings
+//     side by side give every SM scheduler more than one warp;
+//   * a row block [r0, r1) of a pair, starting from a stored key row and leaving the key row of r1 behind
+//     (`top` / `bottom`): the linear-space overflow path recomputes blocks from such checkpoint rows when the
+//     direction matrix of the whole pair does not fit in HBM (rsd_long.inl);
+//   * a range of column panels [w_lo, w_lo + CTAs) of a pair whose panels exceed the co-resident CTAs.
+// Replaces (reference): wagnerFisher + create_paths(dp)[0] for pairs the reference cannot hold (SED:133-271).
+#pragma once
+#include "k_long.cuh"
+
+struct LongJob2 {
+    const uint8_t *a, *b;          // 1 byte / symbol codes on the device (whole sequences)
+    int m, n;                      // whole lengths
+    int r0, r1;                    // source rows of this launch (r0 a multiple of 32; r1 == m or a multiple of 32)
+    int n_panels, n_pad;           // panels of the whole pair, n_pad = n_panels * 32 * C
+    int w_lo, w_cnt;               // panels of this launch
+    const uint32_t *top;           // keys (mod 2^32, H' form) of matrix row r0, columns 1 .. n_pad; NULL = border row (zeros)
+    uint32_t *bottom;              // receives the keys of matrix row r1 (optional)
+    uint32_t *dirs;                // [(r1 - r0 + 15) / 16][n_pad] direction words of this row block (DIRS kernels)
+    unsigned long long *bound;     // [n_panels][bstride] right-most column of every panel, rows r0 .. r1-1, sentinel-preset
+    int bstride;
+    long long *keyacc;             // exact key of the pair's last column, carried from row block to row block
+    double *dist;                  // written by the launch with r1 == m
+    int S;
+};
+
+#define RSD_LONG2_MAX_RINGS 16
+struct LongLaunch2 {
+    const LongJob2 *jobs;                          // device array, ring after ring
+    int n_rings;
+    int ring_job0[RSD_LONG2_MAX_RINGS + 1];        // jobs [ring_job0[g], ring_job0[g+1]) run one after the other on ring g
+    int ring_cta0[RSD_LONG2_MAX_RINGS + 1];        // CTAs [ring_cta0[g], ring_cta0[g+1]) form ring g
+};
+
+// One panel of one job: rows r0 .. r1-1 of the 32*C columns of panel w.  Same arithmetic as k_long_fwd32x2.
+template <int C, bool DIRS>
+__device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, const int lane, const IntCosts *__restrict__ icp,
+                                            uint32_t *s_w, uint32_t *s_pub, uint8_t *s_a) {
+    __syncwarp();
+    for (int k = lane; k < 256; k += 32)
+        s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << J.S) - 1);        // (w << S) - 1, fits (host check)
+    __syncwarp();
+    const int rows = J.r1 - J.r0, n = J.n;
+    const uint8_t *arow = J.a + J.r0;
+    const int col0 = (w * 32 + lane) * C;
+    const bool strip_on = col0 < n;
+    uint32_t H[C], acc[C], bca[C];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int bc = (col0 + c < n) ? J.b[col0 + c] : 0;
+        H[c] = J.top ? J.top[col0 + c] : 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc;
+    }
+    uint32_t last0 = 0u, last1 = H[C - 1];
+    uint32_t prev_recv1 = (J.top && col0 > 0) ? J.top[col0 - 1] : 0u;       // key of (row r0, the column left of this strip)
+    long long full = 0;
+    const unsigned long long *bin = w > 0 ? J.bound + (size_t)(w - 1) * J.bstride : nullptr;
+    unsigned long long *bout = J.bound + (size_t)w * J.bstride;
+    const bool publish = (w + 1 < J.n_panels);
+    uint32_t *dcol = DIRS ? J.dirs + col0 : nullptr;
+    const int steps = (rows + 1) / 2 + 31 + 16;       // + one block so the last rows get published
+    auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? arow[r] : (uint8_t)0; };
+    uint8_t pf0 = fetch(0, 0), pf1 = fetch(0, 1), pf2 = fetch(0, 2);
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += 16) {
+        const uint32_t last_at_block_start = last1;
+        if (publish) {
+            const int r = 2 * (t0 - 47) + lane;
+            if (r >= 0 && r < rows) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
+        }
+        __syncwarp();
+        uint32_t bval = 0u;
+        if (w > 0) {
+            const bool mine = 2 * t0 + lane < rows;
+            unsigned long long raw = 0ull;
+            do {
+                if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
+            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));      // warp-uniform exit (see k_long_fwd)
+            bval = (uint32_t)raw;
+        }
+        unsigned long long codes0 = 0ull, codes1 = 0ull;
+        {
+            s_a[lane] = pf0; s_a[32 + lane] = pf1; s_a[64 + lane] = pf2;
+            pf0 = fetch(t0 + 16, 0); pf1 = fetch(t0 + 16, 1); pf2 = fetch(t0 + 16, 2);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t two = *reinterpret_cast<const uint16_t *>(s_a + 2 * (31 - lane + k));
+                codes0 |= (unsigned long long)(two & 15u) << (4 * k);
+                codes1 |= (unsigned long long)((two >> 8) & 15u) << (4 * k);
+            }
+            __syncwarp();
+        }
+        auto run16 = [&](auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const int i0 = 2 * (t0 + k - lane);
+            const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)rows);
+            const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)rows);
+            const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) << 6, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) << 6;
+            uint32_t w0[C], w1[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0[c]) : "r"(bca[c] + off0));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[c]) : "r"(bca[c] + off1));
+            }
+            uint32_t t2a[C]; int e1a[C];
+            {
+                uint32_t diag = prev_recv1;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t up = H[c];
+                    const uint32_t x = diag + w0[c];
+                    e1a[c] = (int)(x - up);
+                    t2a[c] = up + (uint32_t)min(e1a[c], 0);
+                    diag = up;
+                }
+            }
+            uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
+            uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
+            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, 2 * k), b1 = __shfl_sync(RSD_FULL, bval, 2 * k + 1);
+            if (lane == 0) { recv0 = w > 0 ? b0 : 0u; recv1 = w > 0 ? b1 : 0u; }
+            if (on0) {
+                uint32_t left = recv0, h0[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    [[maybe_unused]] const int e2 = (int)(t2a[c] - left);
+                    h0[c] = t2a[c] + (uint32_t)__viaddmin_s32((int)left, -(int)t2a[c], 0);
+                    left = h0[c];
+                    if constexpr (DIRS) {
+                        acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
+                        acc[c] = __funnelshift_l((uint32_t)e1a[c], acc[c], 1);
+                    }
+                }
+                last0 = left;
+                if (on1) {
+                    uint32_t diag = recv0, left1 = recv1;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const uint32_t up = h0[c];
+                        const uint32_t x = diag + w1[c];
+                        const int e1 = (int)(x - up);
+                        const uint32_t t2 = up + (uint32_t)min(e1, 0);
+                        [[maybe_unused]] const int e2 = (int)(t2 - left1);
+                        const uint32_t hn = t2 + (uint32_t)__viaddmin_s32((int)left1, -(int)t2, 0);
+                        diag = up; H[c] = hn; left1 = hn;
+                        if constexpr (DIRS) {
+                            acc[c] = __funnelshift_l((uint32_t)e2, acc[c], 1);
+                            acc[c] = __funnelshift_l((uint32_t)e1, acc[c], 1);
+                        }
+                    }
+                    last1 = left1;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) H[c] = h0[c];
+                    last1 = last0;
+                }
+                prev_recv1 = recv1;
+                if constexpr (DIRS) {
+                    const int il = on1 ? i0 + 1 : i0;               // last row done in this step
+                    if ((il & 15) == 15 || il == rows - 1) {
+                        const int sh = 2 * (15 - (il & 15));
+                        uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(il >> 4) * J.n_pad);
+#pragma unroll
+                        for (int c = 0; c < C; c += 4)
+                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
+                    }
+                }
+            }
+            if (lane == 31) { s_pub[2 * k] = last0; s_pub[2 * k + 1] = last1; }
+        }
+        };
+        if (2 * (t0 - 31) >= 0 && 2 * (t0 + 15) + 1 <= rows - 1) run16(std::true_type{}); else run16(std::false_type{});
+        __syncwarp();
+        full += (long long)(int)(last1 - last_at_block_start);          // <= 32 bounded row-to-row differences (host check)
+    }
+    if (J.bottom) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) J.bottom[col0 + c] = H[c];
+    }
+    if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
+        // `full` follows column C-1 of this lane from row r0 to row r1; keyacc holds the exact key of that column at row r0
+        const long long at_r1 = *J.keyacc + full;
+        if (J.r1 == J.m) {
+            const int cl = (n - 1) - col0;
+            uint32_t res = 0u;
+#pragma unroll
+            for (int c = 0; c < C; ++c) if (c == cl) res = H[c];
+            const long long hkey = at_r1 + (long long)(int)(res - H[C - 1]);      // column cl lies at most C-1 cells to the left
+            const long long key = hkey + (long long)J.m * (((long long)icp->del << J.S) + 1) + (long long)n * (((long long)icp->ins << J.S) + 1);
+            J.dist[0] = (double)(key >> J.S) / (double)(1 << icp->scale_log2);
+        }
+        *J.keyacc = at_r1;
+    }
+}
+
+template <int C, bool DIRS>
+__global__ void __launch_bounds__(32)
+k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
+    __shared__ uint32_t s_w[256];
+    __shared__ uint32_t s_pub[32];
+    __shared__ __align__(4) uint8_t s_a[96];
+    const int lane = threadIdx.x;
+    int g = 0;
+    while (g + 1 < L.n_rings && (int)blockIdx.x >= L.ring_cta0[g + 1]) ++g;
+    const int wl = (int)blockIdx.x - L.ring_cta0[g];
+    for (int j = L.ring_job0[g]; j < L.ring_job0[g + 1]; ++j) {
+        const LongJob2 J = L.jobs[j];
+        if (wl < J.w_cnt) long2_panel<C, DIRS>(J, J.w_lo + wl, lane, icp, s_w, s_pub, s_a);
+    }
+}
+
+// Traceback of one row block of every pair of a batch: one warp per pair, the tile walk of k_long_traceback, from the
+// state (i, j, pos) the block below left behind down to row r0.  Ops are written sink -> origin from the end of tmp.
+struct LongTb2 {
+    int m, n, r0, n_pad;
+    const uint32_t *dirs;          // direction words of the rows r0 .. (block-relative, as the forward kernel wrote them)
+    uint8_t *tmp;                  // [m + n]
+    int *state;                    // {i, j, pos}; i < 0 = not started (start at (m, n))
+    int32_t *n_ops;
+    int last;                      // this is the pair's top block (r0 == 0): finish the borders and count
+};
+
+__global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restrict__ jobs) {
+    constexpr int TR = 16, TC = 256;
+    __shared__ uint32_t tile[TR][TC];
+    const LongTb2 J = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    int i = J.state[0], j = J.state[1], pos = J.state[2];
+    if (i < 0) { i = J.m; j = J.n; pos = J.m + J.n; }
+    const int r0 = J.r0, n_pad = J.n_pad;
+    while (i > r0 && j > 0) {
+        const int rb_hi = (i - 1 - r0) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
+        const int c_hi = j - 1, c_lo = max(c_hi - TC + 1, 0);
+        const int nr = rb_hi - rb_lo + 1, nc = c_hi - c_lo + 1;
+        {
+            uint32_t v[TR * (TC / 32)];
+#pragma unroll
+            for (int q = 0; q < TR * (TC / 32); ++q) {
+                const int r = q / (TC / 32), c = lane + 32 * (q % (TC / 32));
+                v[q] = (r < nr && c < nc) ? __ldg(J.dirs + (size_t)(rb_lo + r) * n_pad + c_lo + c) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < TR * (TC / 32); ++q) tile[q / (TC / 32)][lane + 32 * (q % (TC / 32))] = v[q];
+        }
+        __syncwarp();
+        const int i_min = r0 + rb_lo * 16;
+        while (i > i_min && j > c_lo) {
+            const int ii = i - lane, jj = j - lane;
+            uint32_t code = 3u;
+            if (ii > i_min && jj > c_lo) code = dir_decode(tile[((ii - 1 - r0) >> 4) - rb_lo][(jj - 1) - c_lo], ii - 1);
+            const unsigned diag_mask = __ballot_sync(RSD_FULL, code == 2u);
+            const int run = diag_mask == 0xffffffffu ? 32 : __ffs(~diag_mask) - 1;
+            if (lane < run) J.tmp[pos - 1 - lane] = (uint8_t)2;
+            pos -= run; i -= run; j -= run;
+            if (run < 32) {
+                const uint32_t nxt = __shfl_sync(RSD_FULL, code, run);
+                if (nxt == 0u) { if (lane == 0) J.tmp[pos - 1] = (uint8_t)0; --pos; --j; }
+                else if (nxt == 1u) { if (lane == 0) J.tmp[pos - 1] = (uint8_t)1; --pos; --i; }
+            }
+        }
+        __syncwarp();
+    }
+    if (J.last) {
+        // borders: row 0 is all inserts (SED:146-164), column 0 all deletes (SED:167-182)
+        const int nj = j, ni = i;
+        for (int k = lane; k < nj; k += 32) J.tmp[pos - 1 - k] = 0;
+        pos -= nj;
+        for (int k = lane; k < ni; k += 32) J.tmp[pos - 1 - k] = 1;
+        pos -= ni; i = 0; j = 0;
+        if (lane == 0) J.n_ops[0] = J.m + J.n - pos;
+    }
+    if (lane == 0) { J.state[0] = i; J.state[1] = j; J.state[2] = pos; }
+}
+
+// packed scripts of a batch: k_long_emit per pair
+struct LongEmit2 { const uint8_t *tmp; int m, n; const int32_t *n_ops; uint8_t *op; int32_t *oi, *oj; };
+
+__global__ void __launch_bounds__(1024) k_long2_emit(const LongEmit2 *__restrict__ jobs) {
+    __shared__ int s_ai[1024], s_bj[1024];
+    __shared__ int carry_i, carry_j;
+    const LongEmit2 J = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int k_ops = J.n_ops[0];
+    const uint8_t *src = J.tmp + ((int64_t)J.m + J.n - k_ops);
+    if (tid == 0) { carry_i = 0; carry_j = 0; }
+    __syncthreads();
+    for (int base = 0; base < k_ops; base += 1024) {
+        const int k = base + tid;
+        const int o = k < k_ops ? src[k] : 3;
+        s_ai[tid] = (o == 1 || o == 2); s_bj[tid] = (o == 0 || o == 2);
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            int xi = tid >= off ? s_ai[tid - off] : 0, xj = tid >= off ? s_bj[tid - off] : 0;
+            __syncthreads();
+            s_ai[tid] += xi; s_bj[tid] += xj;
+            __syncthreads();
+        }
+        const int vi = carry_i + s_ai[tid], vj = carry_j + s_bj[tid];
+        if (k < k_ops) { J.op[k] = (uint8_t)o; if (J.oi) J.oi[k] = vi; if (J.oj) J.oj[k] = vj; }
+        __syncthreads();
+        if (tid == 1023) { carry_i = vi; carry_j = vj; }
+        __syncthreads();
+    }
+}

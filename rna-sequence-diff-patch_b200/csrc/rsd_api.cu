@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -21,6 +22,7 @@
 #include "k_search.cuh"
 #include "k_sim.cuh"
 #include "k_long.cuh"
+#include "k_long2.cuh"
 #include "k_ingest.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -397,7 +399,7 @@ int rsd_ctx::make_plan(const int32_t *d_alen, const int32_t *d_blen, int64_t n_p
     pv.work_counter = pv.totals + 4;
     pv.groups = (int2 *)sl.groups.p;
     pv.C = C; pv.allow_twin = allow_twin;
-    pv.dbg = getenv("RSD_TRACE") ? (unsigned long long *)(pv.totals + 6) : nullptr;
+    pv.dbg = getenv("RSD_TRACE_PLAN") ? (unsigned long long *)(pv.totals + 6) : nullptr;      // synchronises after every plan
     // bin counters are zeroed again by the scan phase, which also resets cursors / ticket / odd-twin
     // slots — so a plan is three kernels and no memsets.  A call that failed between count and
     // fill leaves them dirty: start clean then.
@@ -524,15 +526,17 @@ static int64_t max_len(const int32_t *len, int64_t n) {
     return m;
 }
 
-// true when the sequences are stored in pair order without overlap: start[0] >= 0, start[p] + nwords(len[p]) <=
-// start[p+1], the last one ends inside the buffer.  Then the pairs [p0, p1) own exactly the words [start[p0], start[p1]).
-static bool pair_ordered(const int64_t *start, const int32_t *len, int64_t n, int64_t n_words, int bits) {
-    if (n == 0) return true;
+// true when the sequences [p0, p1) are stored in pair order without overlap: start[p] >= 0, start[p] + nwords(len[p]) <=
+// start[p+1] (the last sequence of the batch ends inside the buffer).  Then the pairs [p0, p1) own exactly the words
+// [start[p0], start[p1]).
+static bool pair_ordered(const int64_t *start, const int32_t *len, int64_t p0, int64_t p1, int64_t n, int64_t n_words, int bits) {
+    if (p1 <= p0) return true;
     const int sh = bits == 2 ? 4 : 3, add = (1 << sh) - 1;
-    int64_t bad = start[0] < 0;
-    for (int64_t p = 0; p + 1 < n; ++p)
+    int64_t bad = start[p0] < 0;
+    const int64_t e = std::min(p1, n - 1);
+    for (int64_t p = p0; p < e; ++p)
         bad |= (int64_t)(start[p] + (((int64_t)len[p] + add) >> sh) > start[p + 1]) | (int64_t)(len[p] < 0);
-    bad |= (int64_t)(len[n - 1] < 0) | (int64_t)(start[n - 1] + (((int64_t)len[n - 1] + add) >> sh) > n_words);
+    if (p1 == n) bad |= (int64_t)(len[n - 1] < 0) | (int64_t)(start[n - 1] + (((int64_t)len[n - 1] + add) >> sh) > n_words);
     return bad == 0;
 }
 
@@ -557,19 +561,21 @@ struct SideIn {
     bool canonical() const { return codes != nullptr || start == nullptr; }
 };
 
-// block sums of nwords(len) (and of len, for raw codes): base[b] = words before block b, base[nblk] = total
-static void block_bases(const int32_t *len, int64_t n, int sh, int64_t *base, int64_t *sym_base) {
+// per-block sums of nwords(len) (and of len, for raw codes) for the blocks [b0, b1): sum[b] = words of block b
+static void block_sums(const int32_t *len, int64_t n, int sh, int64_t b0, int64_t b1, int64_t *sum, int64_t *sym_sum) {
     const int add = (1 << sh) - 1;
-    int64_t acc = 0, sacc = 0;
-    const int64_t nblk = (n + RSD_SCAN_BLOCK - 1) / RSD_SCAN_BLOCK;
-    for (int64_t b = 0; b < nblk; ++b) {
-        base[b] = acc; if (sym_base) sym_base[b] = sacc;
+    for (int64_t b = b0; b < b1; ++b) {
         const int64_t e = std::min<int64_t>(n, (b + 1) * RSD_SCAN_BLOCK);
         int64_t s = 0, ss = 0;
         for (int64_t p = b * RSD_SCAN_BLOCK; p < e; ++p) { s += (len[p] + add) >> sh; ss += len[p]; }
-        acc += s; sacc += ss;
+        sum[b] = s; if (sym_sum) sym_sum[b] = ss;
     }
-    base[nblk] = acc; if (sym_base) sym_base[nblk] = sacc;
+}
+// in place: per-block sums -> exclusive prefix, entry nblk = total
+static void block_prefix(int64_t *tab, int64_t nblk) {
+    int64_t acc = 0;
+    for (int64_t b = 0; b < nblk; ++b) { const int64_t v = tab[b]; tab[b] = acc; acc += v; }
+    tab[nblk] = acc;
 }
 
 static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_t max_m_hint, int64_t max_n_hint, int bits,
@@ -607,13 +613,12 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     for (int s = 0; s < 2; ++s)
         RSD_CUDA(cudaMemcpyAsync(dS[s]->len.p, in[s].len, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cp));
     RSD_CUDA(cudaEventRecord(c->ev_len, cp));
-    // While the lengths travel and the plans are enqueued: block sums of the canonical sides on helper threads.
     const int64_t nblk = (n_pairs + RSD_SCAN_BLOCK - 1) / RSD_SCAN_BLOCK;
     int64_t *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [side][0 words, 1 symbols], nblk + 1 entries each
     int64_t nwords[2] = {in[0].nwords, in[1].nwords};
     const size_t tab_bytes = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
-    std::thread helpers[2];
-    struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 2; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
+    std::thread helpers[4];
+    struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 4; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
     if (any_canon) {
         if (tab_bytes + 64 > c->h_stage_cap) {
             if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -623,10 +628,6 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         }
         RSD_OK_OR_RETURN(c->d_stage.ensure(tab_bytes + 64));
         for (int s = 0; s < 2; ++s) for (int q = 0; q < 2; ++q) tab[s][q] = (int64_t *)c->h_stage + (size_t)(2 * s + q) * (nblk + 1);
-        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-            auto job = [&in, &tab, n_pairs, sh, s] { block_bases(in[s].len, n_pairs, sh, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
-            if (n_pairs >= (1 << 17) && !getenv("RSD_NO_HELPERS")) helpers[s] = std::thread(job); else job();
-        }
     }
     // Large batches are cut into chunks of pairs so the H2D copy of chunk k+1 (copy stream) overlaps
     // the kernels of chunk k (compute stream); sequences are word-aligned and stored in pair order, so
@@ -653,17 +654,63 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         }
     }
     bounds[n_chunks] = n_pairs;
-    // A chunk's copy is the word range [start[p0], start[p1]): with caller-supplied offsets that is only right when
-    // every sequence of the chunk lies inside it, i.e. when sequence p ends at or before the start of sequence p+1
-    // for every p (one branch-free pass over start[] and len[]; ~1 ms per 10^6 pairs and side — callers that
-    // hold rsd_pack's layout pass start == NULL and skip it).  Otherwise the whole batch is copied first.
-    for (int s = 0; s < 2 && n_chunks > 1; ++s)
-        if (!in[s].canonical() && !pair_ordered(in[s].start, in[s].len, n_pairs, in[s].nwords, bits)) { n_chunks = 1; bounds[1] = n_pairs; }
+    // Host-side preparation of a range of pairs, per side.  Canonical layout (start == NULL): the word count of every
+    // block of RSD_SCAN_BLOCK sequences (their prefix gives the chunks' word ranges and seeds the device scan that
+    // rebuilds start[]).  Caller-supplied start[]: a chunk's copy is the word range [start[p0], start[p1]), which is
+    // only right when every sequence ends at or before the start of the next one — one branch-free pass over start[]
+    // and len[]; if it fails anywhere the whole word buffer is copied before the first chunk that needs it.
+    // Both passes are memory-bound reads of the caller's arrays (~1 ms per 10^6 pairs and side on one thread), so
+    // the main thread does the first chunk's range only, sends that chunk's copy on its way, and enqueues the plans
+    // while four helper threads do the rest.
+    std::atomic<int> unordered{0};
+    auto prep = [&](int s, int64_t p0, int64_t p1) {
+        if (p1 <= p0) return;
+        if (in[s].canonical())
+            block_sums(in[s].len, n_pairs, sh, p0 / RSD_SCAN_BLOCK, p1 >= n_pairs ? nblk : p1 / RSD_SCAN_BLOCK, tab[s][0], in[s].codes ? tab[s][1] : nullptr);
+        else if (n_chunks > 1 && !pair_ordered(in[s].start, in[s].len, p0, p1, n_pairs, in[s].nwords, bits))
+            unordered.store(1);
+    };
+    const bool early0 = !any_codes && n_chunks > 1 && bounds[1] > 0;      // chunk 0's copy leaves before the plans are enqueued
+    const int64_t split0 = early0 ? bounds[1] : 0;
+    {
+        const int64_t r0 = split0, r1 = n_pairs;
+        int64_t mid = ((r0 + r1) / 2) / RSD_SCAN_BLOCK * RSD_SCAN_BLOCK;
+        if (mid <= r0 || mid >= r1) mid = r1;
+        const bool threaded = (r1 - r0) >= (1 << 17) && !getenv("RSD_NO_HELPERS");
+        for (int s = 0; s < 2; ++s) {
+            if (!in[s].canonical() && n_chunks == 1) continue;             // nothing to check: one copy of everything
+            if (threaded) {
+                helpers[2 * s] = std::thread([&prep, s, r0, mid] { prep(s, r0, mid); });
+                if (mid < r1) helpers[2 * s + 1] = std::thread([&prep, s, mid, r1] { prep(s, mid, r1); });
+            } else prep(s, r0, r1);
+        }
+        for (int s = 0; s < 2; ++s) prep(s, 0, split0);
+    }
     t_len = now();
     const bool timing = c->timing;
     float kernel_ms = 0.f;
     struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
     c->costs_preloaded = true;
+    for (int s = 0; s < 2; ++s) if (!in[s].codes) RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(in[s].nwords + 8)));
+    // words [w0, w1) of side s and (explicit layout) the start[] slice of the pairs [p0, p1)
+    auto send_words = [&](int s, int64_t w0, int64_t w1, int64_t p0, int64_t p1) -> int {
+        if (w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
+        if (!in[s].canonical())
+            RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+        return RSD_OK;
+    };
+    int first_unsent = 0;
+    if (early0 && !unordered.load()) {
+        for (int s = 0; s < 2; ++s) {
+            int64_t w0 = 0, w1 = 0;
+            if (in[s].canonical()) { for (int64_t b = 0; b < split0 / RSD_SCAN_BLOCK; ++b) w1 += tab[s][0][b]; }
+            else { w0 = in[s].start[0]; w1 = in[s].start[split0]; }
+            if (w1 > in[s].nwords) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its first chunk needs %lld", s, (long long)in[s].nwords, (long long)w1);
+            RSD_OK_OR_RETURN(send_words(s, w0, w1, 0, split0));
+        }
+        RSD_CUDA(cudaEventRecord(c->ev_chunk[0], cp));
+        first_unsent = 1;
+    }
     RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
     auto enqueue_plans = [&]() -> int {
         for (int k = 0; k < n_chunks; ++k) {
@@ -676,13 +723,14 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         c->cur_slot = 0;
         return RSD_OK;
     };
-    // packed input is compute-bound: the plans are enqueued while the helper threads sum; raw codes are copy-bound:
+    // packed input is compute-bound: the plans are enqueued while the helper threads work; raw codes are copy-bound:
     // there the copies go out first
     if (!any_codes) RSD_OK_OR_RETURN(enqueue_plans());
     const double t_plans = now();
-    // the block sums are needed from here on
-    for (int s = 0; s < 2; ++s) if (helpers[s].joinable()) helpers[s].join();
+    for (int s = 0; s < 4; ++s) if (helpers[s].joinable()) helpers[s].join();
     for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+        block_prefix(tab[s][0], nblk);
+        if (in[s].codes) block_prefix(tab[s][1], nblk);
         if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
             return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
                             (long long)in[s].nwords, (long long)tab[s][0][nblk]);
@@ -691,7 +739,7 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     if (any_canon) RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, tab_bytes, cudaMemcpyHostToDevice, cp));
     RSD_CUDA(cudaEventRecord(c->ev_tab, cp));
     for (int s = 0; s < 2; ++s) {
-        RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
+        if (in[s].codes) RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
         RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
         if (in[s].codes) {
             RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
@@ -704,7 +752,11 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         if (p >= n_pairs) return nwords[s];
         return in[s].canonical() ? tab[s][0][p / RSD_SCAN_BLOCK] : in[s].start[p];
     };
-    for (int k = 0; k < n_chunks; ++k) {
+    // a caller-supplied layout that is not in pair order: its whole word buffer goes over before the remaining chunks
+    const bool whole = unordered.load() != 0;
+    if (whole || n_chunks == 1)
+        for (int s = 0; s < 2; ++s) if (!in[s].canonical()) RSD_OK_OR_RETURN(send_words(s, 0, nwords[s], 0, 0));
+    for (int k = first_unsent; k < n_chunks; ++k) {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
         if (p1 <= p0) continue;
         for (int s = 0; s < 2; ++s) {
@@ -713,10 +765,8 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
                 if (s1 > s0) RSD_CUDA(cudaMemcpyAsync((uint8_t *)c->raw_codes[s].p + s0, in[s].codes + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cp));
                 continue;
             }
-            const int64_t w0 = n_chunks == 1 ? 0 : word_at(s, p0), w1 = n_chunks == 1 ? nwords[s] : word_at(s, p1);
-            if (w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
-            if (!in[s].canonical())
-                RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+            const bool sent = !in[s].canonical() && (whole || n_chunks == 1);        // words already on their way: only the start[] slice
+            RSD_OK_OR_RETURN(send_words(s, sent ? 0 : word_at(s, p0), sent ? 0 : word_at(s, p1), p0, p1));
         }
         RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
     }
@@ -1491,9 +1541,11 @@ extern "C" int rsd_db_similarity(rsd_ctx *c, const uint8_t *q_codes, int32_t q_l
 // ------------------------------------------------------------------------------------------------
 // long pair (BASELINE config 4)
 // ------------------------------------------------------------------------------------------------
-extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint8_t *b, int64_t n,
-                             int force_mode, int want_script, int64_t max_ops,
-                             uint8_t *op, int32_t *oi, int32_t *oj, int64_t *n_ops, double *dist, int *mode_out) {
+// first generation: one pair per launch, whole direction matrix resident.  Still the path of the exact-double and fp64
+// kernels (very large or non-dyadic costs) and of the RSD_LONG_V1 / RSD_LONG_R1 / RSD_LONG_WIDE knobs.
+static int long_pair_v1(rsd_ctx *c, const uint8_t *a, int64_t m, const uint8_t *b, int64_t n,
+                        int force_mode, int want_script, int64_t max_ops,
+                        uint8_t *op, int32_t *oi, int32_t *oj, int64_t *n_ops, double *dist, int *mode_out) {
     if (!c) return rsd_fail(RSD_EINVAL, "ctx is NULL");
     if (m < 0 || n < 0 || (m > 0 && !a) || (n > 0 && !b) || !dist) return rsd_fail(RSD_EINVAL, "rsd_long_pair: bad arguments");
     if (m > 0x3fffffff || n > 0x3fffffff) return rsd_fail(RSD_ERANGE, "rsd_long_pair: sequence too long");
@@ -1623,4 +1675,5 @@ extern "C" int rsd_long_pair(rsd_ctx *c, const uint8_t *a, int64_t m, const uint
 // ------------------------------------------------------------------------------------------------
 // several GPUs, one process: sharded database search with an NCCL gather
 // ------------------------------------------------------------------------------------------------
+#include "rsd_long.inl"
 #include "rsd_multi.inl"

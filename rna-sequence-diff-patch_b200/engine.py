@@ -243,6 +243,29 @@ class Engine:
         k = n_ops.value
         return dict(dist=dist.value, op=op[:k], oi=oi[:k], oj=oj[:k], mode=mode.value)
 
+    def long_pairs(self, pairs, want_script: bool = True, force_mode: int = 0):
+        """A batch of long pairs [(a_codes, b_codes), ...] in as few launches as the device memory allows
+        (rsd_long_pairs); -> list of dicts like long_pair."""
+        K = len(pairs)
+        if K == 0:
+            return []
+        A = [np.ascontiguousarray(a, np.uint8) if a.shape[0] else np.zeros(1, np.uint8) for a, _ in pairs]
+        B = [np.ascontiguousarray(b, np.uint8) if b.shape[0] else np.zeros(1, np.uint8) for _, b in pairs]
+        m = np.array([a.shape[0] for a, _ in pairs], np.int64); n = np.array([b.shape[0] for _, b in pairs], np.int64)
+        max_ops = (m + n + 1) if want_script else np.ones(K, np.int64)
+        op = [np.zeros(int(k), np.uint8) for k in max_ops]
+        oi = [np.zeros(int(k), np.int32) for k in max_ops]; oj = [np.zeros(int(k), np.int32) for k in max_ops]
+        parr = lambda xs: (C.c_void_p * K)(*[x.ctypes.data for x in xs])
+        n_ops = np.zeros(K, np.int64); dist = np.zeros(K, np.float64); mode = (C.c_int * K)()
+        check(self._lib.rsd_long_pairs(self._ctx, K, parr(A), ptr(m, _i64), parr(B), ptr(n, _i64), force_mode, int(want_script),
+                                       ptr(np.ascontiguousarray(max_ops, np.int64), _i64), parr(op), parr(oi), parr(oj),
+                                       ptr(n_ops, _i64), ptr(dist, _f64), mode))
+        self.last_mode = mode[0]
+        return [dict(dist=float(dist[k]), op=op[k][:n_ops[k]], oi=oi[k][:n_ops[k]], oj=oj[k][:n_ops[k]], mode=mode[k]) for k in range(K)]
+
+    def long_forward_ms(self) -> float:
+        return float(self._lib.rsd_long_forward_ms(self._ctx))
+
     # ---- introspection -----------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._lib.rsd_launch_count(self._ctx))

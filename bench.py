@@ -463,7 +463,8 @@ def main():
                       "c4_long_pair_50kb": {"gcups_device": e4["device_gcups"], "ms_device": e4["device_s"] * 1e3,
                                             "forward_only_ms": e4["forward_only_device_s"] * 1e3, "n_ops": e4["n_ops"],
                                             "script_equals_oracle_digest": e4["script_equals_oracle_digest"],
-                                            "roofline_frac_5ops": e4["device_gcups"] * 5e-3 / peak if peak else None},
+                                            "roofline_frac_5ops": e4["device_gcups"] * 5e-3 / peak if peak else None,
+                                            "batch": dict(e4["batch"], roofline_frac_5ops=e4["batch"]["device_gcups"] * 5e-3 / peak if peak else None) if e4.get("batch") else None},
                       "c2_iupac_fp64": dict(e2i, roofline_frac_dadd=(e2i["device_gcups"] * 5e-3 / peaks["dadd"]) if peaks.get("dadd") else None,
                                             note="15-letter alphabet, default costs.json (0.66 / 0.83 ...): fp64 kernel in the reference's "
                                                  "operation order; 5 fp64-pipe ops per cell (3 DADD + 2 compares) against the measured DADD issue peak")}

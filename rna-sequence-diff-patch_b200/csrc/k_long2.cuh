@@ -19,13 +19,19 @@ struct LongJob2 {
     int w_lo, w_cnt;               // panels of this launch
     const uint32_t *top;           // keys (mod 2^32, H' form) of matrix row r0, columns 1 .. n_pad; NULL = border row (zeros)
     uint32_t *bottom;              // receives the keys of matrix row r1 (optional)
-    uint32_t *dirs;                // [(r1 - r0 + 15) / 16][n_pad] direction words of this row block (DIRS kernels)
+    uint32_t *dirs;                // [(r1 - r0) / 16 + 8][n_pad] direction words of this row block (DIRS kernels), *skewed*:
+                                   // the word (g, column) of a column held by lane l holds the block rows 16 g - 2 l .. + 15,
+                                   // i.e. what the lane computed in the steps 8 g .. 8 g + 7 — so a whole warp stores its
+                                   // words at the same step, 32 * C * 4 contiguous bytes, with no per-row test
     unsigned long long *bound;     // [n_panels][bstride] right-most column of every panel, rows r0 .. r1-1, sentinel-preset
     int bstride;
     long long *keyacc;             // exact key of the pair's last column, carried from row block to row block
     double *dist;                  // written by the launch with r1 == m
     int S;
 };
+
+// rows of direction-word groups a row block of `rows` rows needs (skew of the last lane + the publication tail)
+__host__ __device__ inline long long long2_dir_groups(long long rows) { return rows / 16 + 8; }
 
 #define RSD_LONG2_MAX_RINGS 16
 struct LongLaunch2 {
@@ -43,7 +49,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     for (int k = lane; k < 256; k += 32)
         s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << J.S) - 1);        // (w << S) - 1, fits (host check)
     __syncwarp();
-    const int rows = J.r1 - J.r0, n = J.n;
+    const int rows = J.r1 - J.r0, n = J.n, n_pad = J.n_pad;
     const uint8_t *arow = J.a + J.r0;
     const int col0 = (w * 32 + lane) * C;
     const bool strip_on = col0 < n;
@@ -51,18 +57,18 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_w);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int bc = (col0 + c < n) ? J.b[col0 + c] : 0;
-        H[c] = J.top ? J.top[col0 + c] : 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc;
+        const int bc = (col0 + c < n) ? __ldg(J.b + col0 + c) : 0;
+        H[c] = J.top ? __ldcg(J.top + col0 + c) : 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc;
     }
     uint32_t last0 = 0u, last1 = H[C - 1];
-    uint32_t prev_recv1 = (J.top && col0 > 0) ? J.top[col0 - 1] : 0u;       // key of (row r0, the column left of this strip)
+    uint32_t prev_recv1 = (J.top && col0 > 0) ? __ldcg(J.top + col0 - 1) : 0u;       // key of (row r0, the column left of this strip)
     long long full = 0;
     const unsigned long long *bin = w > 0 ? J.bound + (size_t)(w - 1) * J.bstride : nullptr;
     unsigned long long *bout = J.bound + (size_t)w * J.bstride;
     const bool publish = (w + 1 < J.n_panels);
     uint32_t *dcol = DIRS ? J.dirs + col0 : nullptr;
     const int steps = (rows + 1) / 2 + 31 + 16;       // + one block so the last rows get published
-    auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? arow[r] : (uint8_t)0; };
+    auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? __ldg(arow + r) : (uint8_t)0; };
     uint8_t pf0 = fetch(0, 0), pf1 = fetch(0, 1), pf2 = fetch(0, 2);
 
 #pragma unroll 1
@@ -97,8 +103,11 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         }
         auto run16 = [&](auto steady_tag) {
         constexpr bool STEADY = decltype(steady_tag)::value;
+#pragma unroll 1
+        for (int k8 = 0; k8 < 16; k8 += 8) {
 #pragma unroll 2
-        for (int k = 0; k < 16; ++k) {
+        for (int kk = 0; kk < 8; ++kk) {
+            const int k = k8 + kk;
             const int i0 = 2 * (t0 + k - lane);
             const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)rows);
             const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)rows);
@@ -157,22 +166,22 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
                     last1 = left1;
                 } else {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) H[c] = h0[c];
+                    for (int c = 0; c < C; ++c) { H[c] = h0[c]; if constexpr (DIRS) acc[c] <<= 2; }      // bit positions follow the step, not the row count
                     last1 = last0;
                 }
                 prev_recv1 = recv1;
-                if constexpr (DIRS) {
-                    const int il = on1 ? i0 + 1 : i0;               // last row done in this step
-                    if ((il & 15) == 15 || il == rows - 1) {
-                        const int sh = 2 * (15 - (il & 15));
-                        uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)(il >> 4) * J.n_pad);
+            } else if constexpr (DIRS && !STEADY) {
 #pragma unroll
-                        for (int c = 0; c < C; c += 4)
-                            dst[c >> 2] = make_uint4(acc[c] << sh, acc[c + 1] << sh, acc[c + 2] << sh, acc[c + 3] << sh);
-                    }
-                }
+                for (int c = 0; c < C; ++c) acc[c] <<= 4;
             }
             if (lane == 31) { s_pub[2 * k] = last0; s_pub[2 * k + 1] = last1; }
+        }
+        if constexpr (DIRS) {
+            // the 16 rows of the last 8 steps, all lanes at once: 32 * C consecutive words of group (t0 + k8) / 8
+            uint4 *dst = reinterpret_cast<uint4 *>(dcol + (size_t)((t0 + k8) >> 3) * n_pad);
+#pragma unroll
+            for (int c = 0; c < C; c += 4) __stcg(dst + (c >> 2), make_uint4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+        }
         }
         };
         if (2 * (t0 - 31) >= 0 && 2 * (t0 + 15) + 1 <= rows - 1) run16(std::true_type{}); else run16(std::false_type{});
@@ -181,7 +190,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     }
     if (J.bottom) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) J.bottom[col0 + c] = H[c];
+        for (int c = 0; c < C; ++c) __stcg(J.bottom + col0 + c, H[c]);
     }
     if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
         // `full` follows column C-1 of this lane from row r0 to row r1; keyacc holds the exact key of that column at row r0
@@ -218,8 +227,8 @@ k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
 // Traceback of one row block of every pair of a batch: one warp per pair, the tile walk of k_long_traceback, from the
 // state (i, j, pos) the block below left behind down to row r0.  Ops are written sink -> origin from the end of tmp.
 struct LongTb2 {
-    int m, n, r0, n_pad;
-    const uint32_t *dirs;          // direction words of the rows r0 .. (block-relative, as the forward kernel wrote them)
+    int m, n, r0, n_pad, C;        // C: columns per lane of the forward kernel (the skew of a column's words is 2 * its lane)
+    const uint32_t *dirs;          // direction words of the rows r0 .. (block-relative and skewed, as the forward kernel wrote them)
     uint8_t *tmp;                  // [m + n]
     int *state;                    // {i, j, pos}; i < 0 = not started (start at (m, n))
     int32_t *n_ops;
@@ -234,8 +243,10 @@ __global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restric
     int i = J.state[0], j = J.state[1], pos = J.state[2];
     if (i < 0) { i = J.m; j = J.n; pos = J.m + J.n; }
     const int r0 = J.r0, n_pad = J.n_pad;
+    const int C = J.C;
     while (i > r0 && j > 0) {
-        const int rb_hi = (i - 1 - r0) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
+        // groups that hold the rows <= i of every column of the tile: row r of a column of lane l sits at position r + 2 l
+        const int rb_hi = (i - 1 - r0 + 62) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
         const int c_hi = j - 1, c_lo = max(c_hi - TC + 1, 0);
         const int nr = rb_hi - rb_lo + 1, nc = c_hi - c_lo + 1;
         {
@@ -249,11 +260,14 @@ __global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restric
             for (int q = 0; q < TR * (TC / 32); ++q) tile[q / (TC / 32)][lane + 32 * (q % (TC / 32))] = v[q];
         }
         __syncwarp();
-        const int i_min = r0 + rb_lo * 16;
+        const int i_min = r0 + rb_lo * 16;               // rows above this (block-relative >= 16 rb_lo) are inside the tile for every lane
         while (i > i_min && j > c_lo) {
             const int ii = i - lane, jj = j - lane;
             uint32_t code = 3u;
-            if (ii > i_min && jj > c_lo) code = dir_decode(tile[((ii - 1 - r0) >> 4) - rb_lo][(jj - 1) - c_lo], ii - 1);
+            if (ii > i_min && jj > c_lo) {
+                const int pos16 = (ii - 1 - r0) + 2 * (((jj - 1) / C) & 31);
+                code = dir_decode(tile[(pos16 >> 4) - rb_lo][(jj - 1) - c_lo], pos16);
+            }
             const unsigned diag_mask = __ballot_sync(RSD_FULL, code == 2u);
             const int run = diag_mask == 0xffffffffu ? 32 : __ffs(~diag_mask) - 1;
             if (lane < run) J.tmp[pos - 1 - lane] = (uint8_t)2;

@@ -44,7 +44,7 @@ size_t long_layout(LongPairPlan &P, unsigned char *base, bool want_script, bool 
     P.keyacc = (long long *)small; P.dist = (double *)(small + 16); P.state = (int *)(small + 32); P.n_ops = (int32_t *)(small + 48);
     P.bound = (unsigned long long *)take((size_t)P.n_panels * (size_t)P.hb * 8);
     if (want_script) {
-        P.dirs = (uint32_t *)take((size_t)((P.hb + 15) / 16) * (size_t)P.n_pad * 4 + 64);
+        P.dirs = (uint32_t *)take((size_t)long2_dir_groups(P.hb) * (size_t)P.n_pad * 4 + 64);
         P.tmp = (uint8_t *)take((size_t)(P.m + P.n) + 64); P.op = (uint8_t *)take((size_t)(P.m + P.n) + 64);
         if (want_ij) { P.oi = (int32_t *)take(4 * (size_t)(P.m + P.n) + 64); P.oj = (int32_t *)take(4 * (size_t)(P.m + P.n) + 64); }
     }
@@ -64,7 +64,6 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     if (n_pairs == 0) return RSD_OK;
     const bool want_ij = want_script && (oi || oj);
     int C = 4;
-    if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8) C = v; }
     std::vector<LongPairPlan> P((size_t)n_pairs);
     std::vector<int> fallback;                       // pairs for rsd_long_pair (fp64 / exact-double keys)
     ModeInfo mi_up{}; bool have_mi = false;
@@ -81,6 +80,19 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         for (int64_t i = 0; i < Q.m; ++i) { if (a[p][i] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15"); sm |= 1u << a[p][i]; }
         for (int64_t j = 0; j < Q.n; ++j) { if (b[p][j] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15"); sm |= 1u << b[p][j]; }
         symmask |= sm; max_m = std::max(max_m, Q.m); max_n = std::max(max_n, Q.n);
+    }
+    // Rings and panel width.  Measured on 50 kb pairs (tools/dbg_long_batch.py, profiles/r02_long_batch.log): one ring per
+    // pair (up to 16) beats fewer, longer rings; throughput peaks at 1500-2000 warps in flight (2.5-3.5 per SM scheduler),
+    // and a lone warp's step time hardly grows from 4 to 8 columns per lane (it is latency-bound), so 8 columns per lane
+    // unless that puts more than ~2000 warps in flight, then 16 (K = 8: 1.56 TCUPS at 8, K = 12: 2.17 TCUPS at 16).
+    int rings_want = 16;
+    {
+        int nk = 0; double sum_n = 0;
+        for (int p = 0; p < n_pairs; ++p) if (!P[p].trivial) { ++nk; sum_n += (double)P[p].n; }
+        if (const char *e = getenv("RSD_LONG_RINGS")) rings_want = std::min(std::max(atoi(e), 1), RSD_LONG2_MAX_RINGS);
+        const double warps8 = nk ? (double)std::min(nk, rings_want) * (sum_n / nk) / 256.0 : 0.0;
+        C = warps8 > 2000.0 ? 16 : 8;
+        if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) C = v; }
     }
     if (symmask) {
         ModeInfo mi;
@@ -121,8 +133,8 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     }
     if (have_mi) {
         RSD_OK_OR_RETURN(c->upload_costs(mi_up, st));
-        const void *kfn_d = C == 4 ? (const void *)k_long2<4, true> : (const void *)k_long2<8, true>;
-        const void *kfn_n = C == 4 ? (const void *)k_long2<4, false> : (const void *)k_long2<8, false>;
+        const void *kfn_d = C == 4 ? (const void *)k_long2<4, true> : C == 8 ? (const void *)k_long2<8, true> : (const void *)k_long2<16, true>;
+        const void *kfn_n = C == 4 ? (const void *)k_long2<4, false> : C == 8 ? (const void *)k_long2<8, false> : (const void *)k_long2<16, false>;
         int per_sm = 0;
         RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn_d, 32, 0));
         int64_t max_ctas = (int64_t)per_sm * c->sm_count;
@@ -165,8 +177,6 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             }
         }
         // ---- batches: consecutive eligible pairs that fit the budget together; a blocked pair runs alone ----
-        int rings_want = 4;
-        if (const char *e = getenv("RSD_LONG_RINGS")) rings_want = std::min(std::max(atoi(e), 1), RSD_LONG2_MAX_RINGS);
         std::vector<int> order;
         for (int p = 0; p < n_pairs; ++p) if (P[p].eligible) order.push_back(p);
         const bool ltrace = getenv("RSD_TRACE") != nullptr;
@@ -205,13 +215,20 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                 return J;
             };
             if (!solo) {
-                // rings: longest pair first, each to the ring with the fewest rows so far
-                const int G = (int)std::min<size_t>((size_t)rings_want, batch.size());
+                // rings: longest pair first, each to the ring with the fewest rows so far; fewer rings when the CTAs
+                // of all rings together would not be co-resident
                 std::vector<int> by = batch;
                 std::sort(by.begin(), by.end(), [&](int x, int y) { return P[x].m * P[x].n > P[y].m * P[y].n; });
-                std::vector<std::vector<int>> ring((size_t)G);
-                std::vector<int64_t> load((size_t)G, 0);
-                for (int p : by) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); ring[(size_t)g].push_back(p); load[(size_t)g] += P[p].m; }
+                std::vector<std::vector<int>> ring;
+                int G = (int)std::min<size_t>((size_t)rings_want, batch.size());
+                for (;; --G) {
+                    ring.assign((size_t)G, {});
+                    std::vector<int64_t> load((size_t)G, 0);
+                    for (int p : by) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); ring[(size_t)g].push_back(p); load[(size_t)g] += P[p].m; }
+                    int64_t cta = 0;
+                    for (int g = 0; g < G; ++g) { int width = 0; for (int p : ring[(size_t)g]) width = std::max(width, P[p].n_panels); cta += width; }
+                    if (cta <= max_ctas || G == 1) break;
+                }
                 Launch L{}; L.job0 = 0; L.dirs = want_script != 0; L.n_rings = G; L.memset_pair = -1; L.tb_pair = -1;
                 int cta = 0;
                 for (int g = 0; g < G; ++g) {
@@ -221,7 +238,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     cta += width;
                 }
                 L.ring_job0[G] = (int)jobs.size(); L.ring_cta0[G] = cta; L.n_jobs = (int)jobs.size();
-                if (cta > max_ctas) return rsd_fail(RSD_ERANGE, "rsd_long_pairs: %d CTAs exceed the %lld co-resident ones (fewer rings: RSD_LONG_RINGS)", cta, (long long)max_ctas);
+                if (cta > max_ctas) return rsd_fail(RSD_ERANGE, "rsd_long_pairs: %d CTAs exceed the %lld co-resident ones", cta, (long long)max_ctas);
                 launches.push_back(L);
             } else {
                 const LongPairPlan &Q = P[batch[0]];
@@ -249,10 +266,10 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             if (want_script) {
                 if (!solo) for (int p : batch) {
                     const LongPairPlan &Q = P[p];
-                    tbs.push_back(LongTb2{(int)Q.m, (int)Q.n, 0, (int)Q.n_pad, Q.dirs, Q.tmp, Q.state, Q.n_ops, 1});
+                    tbs.push_back(LongTb2{(int)Q.m, (int)Q.n, 0, (int)Q.n_pad, C, Q.dirs, Q.tmp, Q.state, Q.n_ops, 1});
                 } else for (const Launch &L : launches) if (L.tb_pair >= 0) {
                     const LongPairPlan &Q = P[L.tb_pair];
-                    tbs.push_back(LongTb2{(int)Q.m, (int)Q.n, L.tb_r0, (int)Q.n_pad, Q.dirs, Q.tmp, Q.state, Q.n_ops, L.tb_r0 == 0 ? 1 : 0});
+                    tbs.push_back(LongTb2{(int)Q.m, (int)Q.n, L.tb_r0, (int)Q.n_pad, C, Q.dirs, Q.tmp, Q.state, Q.n_ops, L.tb_r0 == 0 ? 1 : 0});
                 }
                 for (int p : batch) { const LongPairPlan &Q = P[p]; ems.push_back(LongEmit2{Q.tmp, (int)Q.m, (int)Q.n, Q.n_ops, Q.op, Q.oi, Q.oj}); }
             }

@@ -88,7 +88,7 @@ def test_batch_with_empty_and_mixed_alphabets(R, eng, golden):
     check(res[1], *iupac[0], costs)
 
 
-@pytest.mark.parametrize("budget_mb,maxctas", [(2, 0), (1, 0), (0, 3), (1, 5), (2, 1)])
+@pytest.mark.parametrize("budget_mb,maxctas", [(4, 0), (2, 0), (0, 3), (2, 5), (3, 1)])
 def test_overflow_path_row_blocks_and_panel_ranges(R, eng, golden, monkeypatch, budget_mb, maxctas):
     """RSD_LONG_BUDGET_MB forces the row-block path (checkpoint rows, recomputation bottom to top), RSD_LONG_MAXCTAS the
     panel ranges: distance and script must equal the oracle's, i.e. the one-launch result."""
@@ -112,7 +112,7 @@ def test_overflow_path_in_the_wrap_regime(R, eng, golden, monkeypatch):
     """checkpoint rows hold keys modulo 2^32: with a widened steps field (RSD_LONG_S) they wrap several times between
     the blocks of a 3 k x 3 k matrix"""
     monkeypatch.setenv("RSD_LONG_S", "21")
-    monkeypatch.setenv("RSD_LONG_BUDGET_MB", "1")
+    monkeypatch.setenv("RSD_LONG_BUDGET_MB", "2")
     costs = golden["user_costs"]
     eng.set_costs(costs)
     for a, b in make_pairs(77, [(3000, 3000), (2500, 3300)]):

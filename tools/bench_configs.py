@@ -102,7 +102,7 @@ def c3(eng, n_pairs, reps=3):
             "roundtrip_ok": bool(ok.all()), "oracle_checked_pairs": int(sample.shape[0]), "output": "op bytes + n_ops + dist + ok (oi/oj derivable by prefix sum), pinned host buffers"}
 
 
-def c4(eng, L=50000, reps=3):
+def c4(eng, L=50000, reps=3, batch_pairs=16):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _synth import c4_pair                      # the pair whose oracle script digest is committed (tests/golden/c4_digest.json)
     a, b = c4_pair(m=L)
@@ -129,7 +129,30 @@ def c4(eng, L=50000, reps=3):
         digest_ok = bool(res["dist"] == float.fromhex(rec["dist"]) and sha(res["op"], np.uint8) == rec["op_sha256"]
                          and sha(res["oi"], np.int32) == rec["oi_sha256"] and sha(res["oj"], np.int32) == rec["oj_sha256"])
         assert digest_ok, "C4 script differs from the oracle digest"
-    return {"config": "C4", "script_equals_oracle_digest": digest_ok, "forward_only_device_s": kf, "forward_only_gcups": cells / kf * 1e-9, "m": L, "n": int(b.shape[0]), "cells": cells, "mode": res["mode"], "dist": res["dist"],
+    # the batch form (BASELINE config 4 names "long pairs"): K pairs of the same shape in one rsd_long_pairs call;
+    # pair 0 is the digest pair, every script is checked as a valid path whose cost equals the reported distance
+    batch = None
+    if batch_pairs > 1:
+        pairs = [c4_pair(seed=20260004 + q, m=L) for q in range(batch_pairs)]
+        bt, bk, bf = [], [], []
+        for r in range(reps + 1):
+            t0 = time.perf_counter()
+            out = eng.long_pairs(pairs)
+            if r:
+                bt.append(time.perf_counter() - t0); bk.append(eng.last_kernel_ms()); bf.append(eng.long_forward_ms())
+        bcells = float(sum(float(x.shape[0]) * y.shape[0] for x, y in pairs))
+        assert out[0]["dist"] == res["dist"] and np.array_equal(out[0]["op"], res["op"]) and np.array_equal(out[0]["oj"], res["oj"])
+        for (x, y), o in zip(pairs, out):
+            op, oi, oj = o["op"], o["oi"], o["oj"]
+            assert oi[-1] == x.shape[0] and oj[-1] == y.shape[0]
+            upd = op == 2
+            assert float((op != 2).sum() + (x[oi[upd] - 1] != y[oj[upd] - 1]).sum()) == o["dist"], "script cost != distance"
+            assert np.array_equal(y[oj[op != 1] - 1], y), "patching A with the script does not give B"
+        batch = {"pairs": batch_pairs, "cells": bcells, "device_s": float(np.mean(bk)) * 1e-3, "device_gcups": bcells / (float(np.mean(bk)) * 1e-3) * 1e-9,
+                 "forward_s": float(np.mean(bf)) * 1e-3, "forward_gcups": bcells / (float(np.mean(bf)) * 1e-3) * 1e-9,
+                 "e2e_s": float(np.mean(bt)), "e2e_gcups": bcells / float(np.mean(bt)) * 1e-9,
+                 "checked": "pair 0 == the single-pair result (oracle digest); every script: valid path, cost == distance, patch(A) == B"}
+    return {"config": "C4", "batch": batch, "script_equals_oracle_digest": digest_ok, "forward_only_device_s": kf, "forward_only_gcups": cells / kf * 1e-9, "m": L, "n": int(b.shape[0]), "cells": cells, "mode": res["mode"], "dist": res["dist"],
             "n_ops": int(res["op"].shape[0]), "e2e_gcups": cells / t * 1e-9, "e2e_s": t,
             "device_gcups": cells / k * 1e-9, "device_s": k}
 
@@ -342,6 +365,7 @@ if __name__ == "__main__":
     for w in args.which.split(","):
         t0 = time.perf_counter()
         res = {"c3": lambda: c3(eng, args.c3_pairs), "c4": lambda: c4(eng), "c5": lambda: c5(eng, args.c5_records),
-               "c5i": lambda: c5(eng, args.c5_records, nq=args.c5_iupac_queries, reps=2, iupac=True)}[w]()
+               "c5i": lambda: c5(eng, args.c5_records, nq=args.c5_iupac_queries, reps=2, iupac=True),
+               "c2i": lambda: c2_iupac(eng, 200_000, reps=2), "c4s": lambda: c4(eng, reps=1, batch_pairs=8)}[w]()
         res["wall_incl_datagen_s"] = time.perf_counter() - t0
         print(json.dumps(res), flush=True)

@@ -11,11 +11,19 @@ L = int(os.environ.get("L", 50000))
 pairs = [c4_pair(seed=20260004 + k, m=L) for k in range(16)]
 eng = R.Engine(0); eng.set_costs(cost_tables.default_costs()); eng.set_timing(True)
 single = eng.long_pair(*pairs[0])
-configs = [(1, 1, 4), (2, 2, 4), (4, 4, 4), (4, 2, 4), (8, 8, 4), (8, 4, 4), (8, 2, 4), (8, 1, 4), (8, 8, 8), (8, 4, 8), (8, 2, 8), (16, 8, 4), (16, 4, 4), (16, 4, 8), (16, 2, 8)]
+os.environ["RSD_LONG_V1"] = "1"
+for rep in range(3):
+    eng.long_pair(*pairs[0]); print("first-generation kernel (k_long_fwd32x2), one pair: forward", round(eng.last_kernel_ms(), 3), "ms incl. traceback", flush=True)
+del os.environ["RSD_LONG_V1"]
+# (pairs, rings, columns per lane); 0 = the library's own choice
+configs = [(1, 0, 0), (1, 1, 4), (1, 1, 8), (1, 1, 16), (2, 0, 0), (2, 2, 8), (2, 2, 16), (4, 0, 0), (4, 4, 8), (4, 4, 16), (8, 0, 0), (8, 8, 8), (8, 8, 16),
+           (12, 0, 0), (12, 12, 8), (12, 12, 16), (16, 0, 0), (16, 16, 8), (16, 16, 16)]
 if os.environ.get("CONFIGS"):
     configs = [tuple(int(x) for x in c.split(":")) for c in os.environ["CONFIGS"].split(",")]
 for K, rings, C in configs:
-    os.environ["RSD_LONG_RINGS"] = str(rings); os.environ["RSD_LONG_C"] = str(C)
+    for name, v in (("RSD_LONG_RINGS", rings), ("RSD_LONG_C", C)):
+        if v: os.environ[name] = str(v)
+        else: os.environ.pop(name, None)
     cells = sum(float(a.shape[0]) * b.shape[0] for a, b in pairs[:K])
     for want in (False, True):
         best = 1e9; fwd = 0

@@ -583,7 +583,7 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     const bool trace = getenv("RSD_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_in = now();
-    double t_len = 0, t_cost = 0, t_copy = 0, t_comp = 0;
+    double t_len = 0, t_cost = 0, t_first = 0, t_comp = 0;
     cudaStream_t st = c->stream, cp = c->copy_stream;
     const int64_t max_m = max_m_hint > 0 ? max_m_hint : max_len(in[0].len, n_pairs);
     const int64_t max_n = max_n_hint > 0 ? max_n_hint : max_len(in[1].len, n_pairs);
@@ -602,6 +602,7 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     for (int s = 0; s < 2; ++s) {
         RSD_OK_OR_RETURN(dS[s]->start.ensure(sizeof(int64_t) * (size_t)n_pairs));
         RSD_OK_OR_RETURN(dS[s]->len.ensure(sizeof(int32_t) * (size_t)n_pairs));
+        if (!in[s].codes) RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(in[s].nwords + 8)));
     }
     RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_pairs));
     // the previous call's kernels may still read these buffers: order the copy stream after them
@@ -617,8 +618,8 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     int64_t *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [side][0 words, 1 symbols], nblk + 1 entries each
     int64_t nwords[2] = {in[0].nwords, in[1].nwords};
     const size_t tab_bytes = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
-    std::thread helpers[4];
-    struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 4; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
+    std::thread helpers[2];
+    struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 2; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
     if (any_canon) {
         if (tab_bytes + 64 > c->h_stage_cap) {
             if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -654,63 +655,11 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         }
     }
     bounds[n_chunks] = n_pairs;
-    // Host-side preparation of a range of pairs, per side.  Canonical layout (start == NULL): the word count of every
-    // block of RSD_SCAN_BLOCK sequences (their prefix gives the chunks' word ranges and seeds the device scan that
-    // rebuilds start[]).  Caller-supplied start[]: a chunk's copy is the word range [start[p0], start[p1]), which is
-    // only right when every sequence ends at or before the start of the next one — one branch-free pass over start[]
-    // and len[]; if it fails anywhere the whole word buffer is copied before the first chunk that needs it.
-    // Both passes are memory-bound reads of the caller's arrays (~1 ms per 10^6 pairs and side on one thread), so
-    // the main thread does the first chunk's range only, sends that chunk's copy on its way, and enqueues the plans
-    // while four helper threads do the rest.
-    std::atomic<int> unordered{0};
-    auto prep = [&](int s, int64_t p0, int64_t p1) {
-        if (p1 <= p0) return;
-        if (in[s].canonical())
-            block_sums(in[s].len, n_pairs, sh, p0 / RSD_SCAN_BLOCK, p1 >= n_pairs ? nblk : p1 / RSD_SCAN_BLOCK, tab[s][0], in[s].codes ? tab[s][1] : nullptr);
-        else if (n_chunks > 1 && !pair_ordered(in[s].start, in[s].len, p0, p1, n_pairs, in[s].nwords, bits))
-            unordered.store(1);
-    };
-    const bool early0 = !any_codes && n_chunks > 1 && bounds[1] > 0;      // chunk 0's copy leaves before the plans are enqueued
-    const int64_t split0 = early0 ? bounds[1] : 0;
-    {
-        const int64_t r0 = split0, r1 = n_pairs;
-        int64_t mid = ((r0 + r1) / 2) / RSD_SCAN_BLOCK * RSD_SCAN_BLOCK;
-        if (mid <= r0 || mid >= r1) mid = r1;
-        const bool threaded = (r1 - r0) >= (1 << 17) && !getenv("RSD_NO_HELPERS");
-        for (int s = 0; s < 2; ++s) {
-            if (!in[s].canonical() && n_chunks == 1) continue;             // nothing to check: one copy of everything
-            if (threaded) {
-                helpers[2 * s] = std::thread([&prep, s, r0, mid] { prep(s, r0, mid); });
-                if (mid < r1) helpers[2 * s + 1] = std::thread([&prep, s, mid, r1] { prep(s, mid, r1); });
-            } else prep(s, r0, r1);
-        }
-        for (int s = 0; s < 2; ++s) prep(s, 0, split0);
-    }
     t_len = now();
     const bool timing = c->timing;
     float kernel_ms = 0.f;
     struct SlotReset { rsd_ctx *c; ~SlotReset() { c->cur_slot = 0; c->costs_preloaded = false; c->cur_ev0 = c->ev0; c->cur_ev1 = c->ev1; } } slot_reset{c};
     c->costs_preloaded = true;
-    for (int s = 0; s < 2; ++s) if (!in[s].codes) RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(in[s].nwords + 8)));
-    // words [w0, w1) of side s and (explicit layout) the start[] slice of the pairs [p0, p1)
-    auto send_words = [&](int s, int64_t w0, int64_t w1, int64_t p0, int64_t p1) -> int {
-        if (w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
-        if (!in[s].canonical())
-            RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
-        return RSD_OK;
-    };
-    int first_unsent = 0;
-    if (early0 && !unordered.load()) {
-        for (int s = 0; s < 2; ++s) {
-            int64_t w0 = 0, w1 = 0;
-            if (in[s].canonical()) { for (int64_t b = 0; b < split0 / RSD_SCAN_BLOCK; ++b) w1 += tab[s][0][b]; }
-            else { w0 = in[s].start[0]; w1 = in[s].start[split0]; }
-            if (w1 > in[s].nwords) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its first chunk needs %lld", s, (long long)in[s].nwords, (long long)w1);
-            RSD_OK_OR_RETURN(send_words(s, w0, w1, 0, split0));
-        }
-        RSD_CUDA(cudaEventRecord(c->ev_chunk[0], cp));
-        first_unsent = 1;
-    }
     RSD_CUDA(cudaStreamWaitEvent(st, c->ev_len, 0));
     auto enqueue_plans = [&]() -> int {
         for (int k = 0; k < n_chunks; ++k) {
@@ -721,86 +670,16 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
                                               symmask, force_mode, (double *)c->out_f64.p + p0, mode_out, st));
         }
         c->cur_slot = 0;
+        RSD_CUDA(cudaEventRecord(c->ev_plans, st));
+        RSD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_plans, 0));
         return RSD_OK;
     };
-    // packed input is compute-bound: the plans are enqueued while the helper threads work; raw codes are copy-bound:
-    // there the copies go out first
-    if (!any_codes) RSD_OK_OR_RETURN(enqueue_plans());
-    const double t_plans = now();
-    for (int s = 0; s < 4; ++s) if (helpers[s].joinable()) helpers[s].join();
-    for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-        block_prefix(tab[s][0], nblk);
-        if (in[s].codes) block_prefix(tab[s][1], nblk);
-        if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
-            return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
-                            (long long)in[s].nwords, (long long)tab[s][0][nblk]);
-        nwords[s] = tab[s][0][nblk];
-    }
-    if (any_canon) RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, tab_bytes, cudaMemcpyHostToDevice, cp));
-    RSD_CUDA(cudaEventRecord(c->ev_tab, cp));
-    for (int s = 0; s < 2; ++s) {
-        if (in[s].codes) RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
-        RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
-        if (in[s].codes) {
-            RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
-            RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
-        }
-    }
     unsigned long long *d_bad = (unsigned long long *)((unsigned char *)c->d_stage.p + tab_bytes);       // {bad sequence + 1, symbols seen}
-    if (any_codes) RSD_CUDA(cudaMemsetAsync(d_bad, 0, 16, st));
-    auto word_at = [&](int s, int64_t p) -> int64_t {
-        if (p >= n_pairs) return nwords[s];
-        return in[s].canonical() ? tab[s][0][p / RSD_SCAN_BLOCK] : in[s].start[p];
-    };
-    // a caller-supplied layout that is not in pair order: its whole word buffer goes over before the remaining chunks
-    const bool whole = unordered.load() != 0;
-    if (whole || n_chunks == 1)
-        for (int s = 0; s < 2; ++s) if (!in[s].canonical()) RSD_OK_OR_RETURN(send_words(s, 0, nwords[s], 0, 0));
-    for (int k = first_unsent; k < n_chunks; ++k) {
+    // the distance kernel of chunk k and the copy of its results; chunk kernels alternate between two streams: the next
+    // chunk's blocks move in while the last tasks of the previous chunk drain, so a chunk boundary costs no idle SMs
+    auto launch_chunk = [&](int k, cudaStream_t sk) -> int {
         const int64_t p0 = bounds[k], p1 = bounds[k + 1];
-        if (p1 <= p0) continue;
-        for (int s = 0; s < 2; ++s) {
-            if (in[s].codes) {
-                const int64_t s0 = tab[s][1][p0 / RSD_SCAN_BLOCK], s1 = p1 >= n_pairs ? tab[s][1][nblk] : tab[s][1][p1 / RSD_SCAN_BLOCK];
-                if (s1 > s0) RSD_CUDA(cudaMemcpyAsync((uint8_t *)c->raw_codes[s].p + s0, in[s].codes + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cp));
-                continue;
-            }
-            const bool sent = !in[s].canonical() && (whole || n_chunks == 1);        // words already on their way: only the start[] slice
-            RSD_OK_OR_RETURN(send_words(s, sent ? 0 : word_at(s, p0), sent ? 0 : word_at(s, p1), p0, p1));
-        }
-        RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
-    }
-    t_copy = now();
-    if (any_codes) RSD_OK_OR_RETURN(enqueue_plans());
-    if (any_canon) {
-        RSD_CUDA(cudaStreamWaitEvent(st, c->ev_tab, 0));
-        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-            const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
-            k_starts_from_len<<<(unsigned)nblk, 1024, 0, st>>>((const int32_t *)dS[s]->len.p, n_pairs, sh, dtab, (int64_t *)dS[s]->start.p,
-                                                              in[s].codes ? dtab + (nblk + 1) : nullptr, in[s].codes ? (int64_t *)c->sym_start[s].p : nullptr);
-            c->launches += 1;
-        }
-    }
-    RSD_CUDA(cudaEventRecord(c->ev_plans, st));
-    RSD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_plans, 0));
-    // chunk kernels alternate between two streams: the next chunk's blocks move in while the last tasks of the
-    // previous chunk drain, so a chunk boundary costs no idle SMs
-    for (int k = 0; k < n_chunks; ++k) {
-        const int64_t p0 = bounds[k], p1 = bounds[k + 1];
-        if (p1 <= p0) continue;
-        cudaStream_t sk = (k & 1) ? c->stream2 : st;
         c->cur_slot = k;
-        RSD_CUDA(cudaStreamWaitEvent(sk, c->ev_chunk[k], 0));
-        for (int s = 0; s < 2; ++s) if (in[s].codes) {                  // raw codes of the chunk -> packed words, on the device
-            const int64_t w0 = word_at(s, p0), w1 = word_at(s, p1);
-            if (w1 <= w0) continue;
-            const unsigned grid = (unsigned)((w1 - w0 + 255) / 256);
-            if (bits == 2) k_pack_codes<2><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
-                                                               (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
-            else k_pack_codes<4><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
-                                                      (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
-            c->launches += 1;
-        }
         c->cur_ev0 = c->ev_t0[k]; c->cur_ev1 = c->ev_t1[k];
         RSD_OK_OR_RETURN(c->distance_launch((const uint32_t *)dS[0]->words.p, (const int64_t *)dS[0]->start.p + p0, (const int32_t *)dS[0]->len.p + p0,
                                             (const uint32_t *)dS[1]->words.p, (const int64_t *)dS[1]->start.p + p0, (const int32_t *)dS[1]->len.p + p0,
@@ -809,10 +688,143 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
         RSD_CUDA(cudaEventRecord(c->ev_done[k], sk));
         RSD_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
         RSD_CUDA(cudaMemcpyAsync(out + p0, (double *)c->out_f64.p + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, c->d2h_stream));
+        return RSD_OK;
+    };
+    volatile unsigned long long *h_bad = nullptr;
+
+    if (!any_codes) {
+        // ---- packed words: everything a chunk needs is prepared, copied and launched chunk by chunk -----------------
+        // Host-side preparation of a chunk, per side.  Canonical layout (start == NULL): the word count of every block
+        // of RSD_SCAN_BLOCK sequences — their running sum gives the chunk's word range and seeds the device scan that
+        // rebuilds start[] (so start[], 8 bytes per sequence, never crosses PCIe).  Caller-supplied start[]: a chunk's
+        // copy is the word range [start[p0], start[p1]), which is only right when every sequence ends at or before the
+        // start of the next one — one branch-free pass over start[] and len[]; from the first chunk that fails it the
+        // whole word buffer is sent instead.  Both passes are memory-bound reads of the caller's arrays (0.3-1 ms per
+        // 10^6 pairs and side): done per chunk on this thread they hide behind the kernels of the chunks before, and
+        // only the first chunk's share (7 % of the batch) sits in front of the first copy.
+        int64_t wacc[2] = {0, 0};
+        bool whole[2] = {false, false};                  // side sent as one buffer (not in pair order, or a single chunk)
+        bool plans_done = false;
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+            if (p1 <= p0) continue;
+            const int64_t b0 = p0 / RSD_SCAN_BLOCK, b1 = p1 >= n_pairs ? nblk : p1 / RSD_SCAN_BLOCK;
+            for (int s = 0; s < 2; ++s) {
+                if (in[s].canonical()) {
+                    block_sums(in[s].len, n_pairs, sh, b0, b1, tab[s][0], nullptr);
+                    const int64_t w0 = wacc[s];
+                    for (int64_t b = b0; b < b1; ++b) { const int64_t v = tab[s][0][b]; tab[s][0][b] = wacc[s]; wacc[s] += v; }
+                    if (wacc[s] > in[s].nwords)
+                        return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need at least %lld (canonical layout)", s,
+                                        (long long)in[s].nwords, (long long)wacc[s]);
+                    int64_t *dtab = (int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
+                    RSD_CUDA(cudaMemcpyAsync(dtab + b0, tab[s][0] + b0, sizeof(int64_t) * (size_t)(b1 - b0), cudaMemcpyHostToDevice, cp));
+                    if (wacc[s] > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(wacc[s] - w0), cudaMemcpyHostToDevice, cp));
+                    if (p1 >= n_pairs) { nwords[s] = wacc[s]; RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp)); }
+                } else {
+                    if (!whole[s] && (n_chunks == 1 || !pair_ordered(in[s].start, in[s].len, p0, p1, n_pairs, in[s].nwords, bits))) {
+                        whole[s] = true;
+                        if (nwords[s] > 0) RSD_CUDA(cudaMemcpyAsync(dS[s]->words.p, in[s].words, sizeof(uint32_t) * (size_t)nwords[s], cudaMemcpyHostToDevice, cp));
+                    }
+                    if (!whole[s]) {
+                        const int64_t w0 = in[s].start[p0], w1 = p1 >= n_pairs ? nwords[s] : in[s].start[p1];
+                        if (w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
+                    }
+                    RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+                    if (p1 >= n_pairs) RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
+                }
+            }
+            RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
+            if (!plans_done) { t_first = now(); RSD_OK_OR_RETURN(enqueue_plans()); plans_done = true; }
+            cudaStream_t sk = (k & 1) ? c->stream2 : st;
+            RSD_CUDA(cudaStreamWaitEvent(sk, c->ev_chunk[k], 0));
+            for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+                const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
+                k_starts_from_len<<<(unsigned)(b1 - b0), 1024, 0, sk>>>((const int32_t *)dS[s]->len.p + p0, p1 - p0, sh, dtab + b0, (int64_t *)dS[s]->start.p + p0, nullptr, nullptr);
+                c->launches += 1;
+            }
+            RSD_OK_OR_RETURN(launch_chunk(k, sk));
+        }
+    } else {
+        // ---- raw codes: copy-bound, so the copies go out first; block sums of both sides on helper threads ---------
+        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+            auto job = [&in, &tab, n_pairs, sh, nblk, s] { block_sums(in[s].len, n_pairs, sh, 0, nblk, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
+            if (n_pairs >= (1 << 17) && !getenv("RSD_NO_HELPERS")) helpers[s] = std::thread(job); else job();
+        }
+        for (int s = 0; s < 2; ++s) if (helpers[s].joinable()) helpers[s].join();
+        bool whole[2] = {false, false};
+        for (int s = 0; s < 2; ++s) {
+            if (in[s].canonical()) {
+                block_prefix(tab[s][0], nblk);
+                if (in[s].codes) block_prefix(tab[s][1], nblk);
+                if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
+                    return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
+                                    (long long)in[s].nwords, (long long)tab[s][0][nblk]);
+                nwords[s] = tab[s][0][nblk];
+            } else if (n_chunks == 1 || !pair_ordered(in[s].start, in[s].len, 0, n_pairs, n_pairs, in[s].nwords, bits)) whole[s] = true;
+        }
+        RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, tab_bytes, cudaMemcpyHostToDevice, cp));
+        RSD_CUDA(cudaEventRecord(c->ev_tab, cp));
+        for (int s = 0; s < 2; ++s) {
+            if (in[s].codes) {
+                RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
+                RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
+                RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
+            }
+            RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
+            if (whole[s] && nwords[s] > 0) RSD_CUDA(cudaMemcpyAsync(dS[s]->words.p, in[s].words, sizeof(uint32_t) * (size_t)nwords[s], cudaMemcpyHostToDevice, cp));
+        }
+        RSD_CUDA(cudaMemsetAsync(d_bad, 0, 16, st));
+        auto word_at = [&](int s, int64_t p) -> int64_t {
+            if (p >= n_pairs) return nwords[s];
+            return in[s].canonical() ? tab[s][0][p / RSD_SCAN_BLOCK] : in[s].start[p];
+        };
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+            if (p1 <= p0) continue;
+            for (int s = 0; s < 2; ++s) {
+                if (in[s].codes) {
+                    const int64_t s0 = tab[s][1][p0 / RSD_SCAN_BLOCK], s1 = p1 >= n_pairs ? tab[s][1][nblk] : tab[s][1][p1 / RSD_SCAN_BLOCK];
+                    if (s1 > s0) RSD_CUDA(cudaMemcpyAsync((uint8_t *)c->raw_codes[s].p + s0, in[s].codes + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cp));
+                    continue;
+                }
+                const int64_t w0 = word_at(s, p0), w1 = word_at(s, p1);
+                if (!whole[s] && w1 > w0) RSD_CUDA(cudaMemcpyAsync((uint32_t *)dS[s]->words.p + w0, in[s].words + w0, sizeof(uint32_t) * (size_t)(w1 - w0), cudaMemcpyHostToDevice, cp));
+                if (!in[s].canonical())
+                    RSD_CUDA(cudaMemcpyAsync((int64_t *)dS[s]->start.p + p0, in[s].start + p0, sizeof(int64_t) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, cp));
+            }
+            RSD_CUDA(cudaEventRecord(c->ev_chunk[k], cp));
+        }
+        t_first = now();
+        RSD_CUDA(cudaStreamWaitEvent(st, c->ev_tab, 0));
+        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+            const int64_t *dtab = (const int64_t *)c->d_stage.p + (size_t)(2 * s) * (nblk + 1);
+            k_starts_from_len<<<(unsigned)nblk, 1024, 0, st>>>((const int32_t *)dS[s]->len.p, n_pairs, sh, dtab, (int64_t *)dS[s]->start.p,
+                                                              in[s].codes ? dtab + (nblk + 1) : nullptr, in[s].codes ? (int64_t *)c->sym_start[s].p : nullptr);
+            c->launches += 1;
+        }
+        RSD_OK_OR_RETURN(enqueue_plans());
+        for (int k = 0; k < n_chunks; ++k) {
+            const int64_t p0 = bounds[k], p1 = bounds[k + 1];
+            if (p1 <= p0) continue;
+            cudaStream_t sk = (k & 1) ? c->stream2 : st;
+            RSD_CUDA(cudaStreamWaitEvent(sk, c->ev_chunk[k], 0));
+            for (int s = 0; s < 2; ++s) if (in[s].codes) {                  // raw codes of the chunk -> packed words, on the device
+                const int64_t w0 = word_at(s, p0), w1 = word_at(s, p1);
+                if (w1 <= w0) continue;
+                const unsigned grid = (unsigned)((w1 - w0 + 255) / 256);
+                if (bits == 2) k_pack_codes<2><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
+                                                                   (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
+                else k_pack_codes<4><<<grid, 256, 0, sk>>>((const uint8_t *)c->raw_codes[s].p, (const int64_t *)c->sym_start[s].p, (const int64_t *)dS[s]->start.p,
+                                                          (const int32_t *)dS[s]->len.p, n_pairs, w0, w1, 0, (uint32_t *)dS[s]->words.p, d_bad, nullptr);
+                c->launches += 1;
+            }
+            RSD_OK_OR_RETURN(launch_chunk(k, sk));
+        }
+        // the d2h stream already waits for every chunk's kernels (ev_done[k]), pack kernels included
+        h_bad = (volatile unsigned long long *)((unsigned char *)c->h_stage + tab_bytes);
+        RSD_CUDA(cudaMemcpyAsync((void *)h_bad, d_bad, 16, cudaMemcpyDeviceToHost, c->d2h_stream));
     }
-    // the d2h stream already waits for every chunk's kernels (ev_done[k] above), pack kernels included
-    volatile unsigned long long *h_bad = any_codes ? (volatile unsigned long long *)((unsigned char *)c->h_stage + tab_bytes) : nullptr;
-    if (any_codes) RSD_CUDA(cudaMemcpyAsync((void *)h_bad, d_bad, 16, cudaMemcpyDeviceToHost, c->d2h_stream));
     t_comp = now();
     RSD_CUDA(cudaStreamSynchronize(c->d2h_stream));
     RSD_CUDA(cudaStreamSynchronize(cp));
@@ -820,8 +832,8 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     RSD_CUDA(cudaStreamSynchronize(st));
     if (h_bad && h_bad[0])
         return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a symbol code of sequence %llu does not fit %d bits", (unsigned long long)h_bad[0] - 1ull, bits);
-    if (trace) fprintf(stderr, "[rsd trace] host ms: classify+costs %.3f, lengths enqueued %.3f, plans enqueued %.3f, block sums joined + copies enqueued %.3f, kernels enqueued %.3f, wait %.3f\n",
-                       t_cost - t_in, t_len - t_cost, t_plans - t_len, t_copy - t_plans, t_comp - t_copy, now() - t_comp);
+    if (trace) fprintf(stderr, "[rsd trace] host ms: classify+costs %.3f, lengths enqueued %.3f, first chunk prepared and sent %.3f, all chunks enqueued %.3f, wait %.3f\n",
+                       t_cost - t_in, t_len - t_cost, t_first - t_len, t_comp - t_first, now() - t_comp);
     if (timing) {
         for (int k = 0; k < n_chunks; ++k) {
             if (bounds[k + 1] <= bounds[k]) continue;

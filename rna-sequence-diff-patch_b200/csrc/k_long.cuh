@@ -44,6 +44,14 @@ __device__ __forceinline__ unsigned long long ld_poll_u64(const unsigned long lo
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// the fp64 kernel publishes (steps, then fence, then key): its consumer reads the key with acquire semantics so the
+// steps word it reads next is the one written before the key (PTX memory model; the relaxed poll is enough for the
+// integer kernels, whose boundary cell is a single 64-bit word)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_cg_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -115,7 +123,7 @@ k_long_fwd(LongArgs la, const IntCosts *__restrict__ icp, const F64Costs *__rest
             const bool mine = lane < 16 && t0 + lane < m;
             unsigned long long raw = 0ull;
             do {
-                if (mine) raw = ld_poll_u64(bin + t0 + lane);
+                if (mine) raw = F64 ? ld_acquire_u64(bin + t0 + lane) : ld_poll_u64(bin + t0 + lane);
             } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));
             if (mine) {
                 bval = __longlong_as_double((long long)raw);

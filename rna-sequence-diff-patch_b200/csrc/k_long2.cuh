@@ -46,8 +46,10 @@ template <int C, bool DIRS>
 __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, const int lane, const IntCosts *__restrict__ icp,
                                             uint32_t *s_w, uint32_t *s_pub, uint8_t *s_a) {
     __syncwarp();
+    // table rows are 20 words apart: the 16 entries of an A/G/C/U pair fall into 16 different banks (rows of 16 words
+    // put symbols 0 and 2, 1 and 3 on the same banks: 2-way conflicts on most lookups of ACGU data, ncu)
     for (int k = lane; k < 256; k += 32)
-        s_w[k] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << J.S) - 1);        // (w << S) - 1, fits (host check)
+        s_w[(k >> 4) * 20 + (k & 15)] = (uint32_t)(((long long)icp->w[k >> 4][k & 15] << J.S) - 1);        // (w << S) - 1, fits (host check)
     __syncwarp();
     const int rows = J.r1 - J.r0, n = J.n, n_pad = J.n_pad;
     const uint8_t *arow = J.a + J.r0;
@@ -70,6 +72,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     const int steps = (rows + 1) / 2 + 31 + 16;       // + one block so the last rows get published
     auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? __ldg(arow + r) : (uint8_t)0; };
     uint8_t pf0 = fetch(0, 0), pf1 = fetch(0, 1), pf2 = fetch(0, 2);
+    unsigned long long raw_next = (w > 0 && lane < rows) ? ld_poll_u64(bin + lane) : 0ull;
 
 #pragma unroll 1
     for (int t0 = 0; t0 < steps; t0 += 16) {
@@ -79,14 +82,18 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
             if (r >= 0 && r < rows) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
         }
         __syncwarp();
+        // The 32 boundary rows of this block were requested one block ahead (raw_next): once the panel runs far enough
+        // behind its left neighbour they have arrived by now and the L2 round trip of the poll is off the critical
+        // path; a sentinel means "not published yet" and is polled again.
         uint32_t bval = 0u;
         if (w > 0) {
             const bool mine = 2 * t0 + lane < rows;
-            unsigned long long raw = 0ull;
-            do {
+            unsigned long long raw = raw_next;
+            while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL)) {       // warp-uniform exit (see k_long_fwd)
                 if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
-            } while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL));      // warp-uniform exit (see k_long_fwd)
+            }
             bval = (uint32_t)raw;
+            raw_next = (2 * (t0 + 16) + lane < rows) ? ld_poll_u64(bin + 2 * (t0 + 16) + lane) : 0ull;
         }
         unsigned long long codes0 = 0ull, codes1 = 0ull;
         {
@@ -111,7 +118,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
             const int i0 = 2 * (t0 + k - lane);
             const bool on0 = STEADY || (strip_on && (unsigned)i0 < (unsigned)rows);
             const bool on1 = STEADY || (strip_on && (unsigned)(i0 + 1) < (unsigned)rows);
-            const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) << 6, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) << 6;
+            const uint32_t off0 = ((uint32_t)(codes0 >> (4 * k)) & 15u) * 80u, off1 = ((uint32_t)(codes1 >> (4 * k)) & 15u) * 80u;
             uint32_t w0[C], w1[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -211,7 +218,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
 template <int C, bool DIRS>
 __global__ void __launch_bounds__(32)
 k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
-    __shared__ uint32_t s_w[256];
+    __shared__ uint32_t s_w[320];
     __shared__ uint32_t s_pub[32];
     __shared__ __align__(4) uint8_t s_a[96];
     const int lane = threadIdx.x;

@@ -127,3 +127,24 @@ def test_overflow_budget_too_small_is_an_error(R, eng, golden, monkeypatch):
     with pytest.raises(R.RsdError):
         # 0 MB: nothing fits, not even 32-row blocks
         eng.long_pair(a, b)
+
+
+def test_overflow_path_equals_one_launch_at_60kb(R, eng, golden, monkeypatch):
+    """60 kb x 60 kb, beyond what the CPU oracle does in test time: the row-block / panel-range path must return the
+    distance and script of the one-launch path (itself pinned to the oracle digest at 50 kb), for budgets that give
+    3 and 12 row blocks and for panel ranges of 100 CTAs."""
+    from _synth import c4_pair
+    a, b = c4_pair(seed=6060, m=60000)
+    eng.set_costs(golden["default_costs"])
+    ref = eng.long_pair(a, b)
+    assert ref["oi"][-1] == a.shape[0] and ref["oj"][-1] == b.shape[0]
+    for env in ({"RSD_LONG_BUDGET_MB": "500"}, {"RSD_LONG_BUDGET_MB": "120"}, {"RSD_LONG_MAXCTAS": "100"},
+                {"RSD_LONG_BUDGET_MB": "300", "RSD_LONG_MAXCTAS": "77"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = eng.long_pair(a, b)
+        assert res["dist"] == ref["dist"]
+        assert np.array_equal(res["op"], ref["op"]) and np.array_equal(res["oi"], ref["oi"]) and np.array_equal(res["oj"], ref["oj"])
+        assert eng.long_pair(a, b, want_script=False)["dist"] == ref["dist"]
+        for k in env:
+            monkeypatch.delenv(k)

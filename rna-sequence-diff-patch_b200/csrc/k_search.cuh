@@ -129,15 +129,27 @@ k_search_twin16(const uint32_t *__restrict__ db_words, const int64_t *__restrict
                 all_scores[(size_t)q * all_stride + (gA - global_base)] = sA;
                 if (hasB) all_scores[(size_t)q * all_stride + (gB - global_base)] = sB;
             }
-            if (tk.k > 0 && live) {
+            if (tk.k > 0) {
+                // candidates are appended with one atomic per warp (ballot + rank): in the seeding chunk every record is a
+                // candidate of every query, and 4096 same-address atomics per query were 3/4 of that launch (ncu: 177 us)
                 const double ts = s_tau[q]; const long long ti = s_taui[q];
-                if (sA > ts || (sA == ts && gA <= ti)) {
-                    const int slot = atomicAdd(&tk.cand_n[q], 1);
-                    if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
-                }
-                if (hasB && (sB > ts || (sB == ts && gB <= ti))) {
-                    const int slot = atomicAdd(&tk.cand_n[q], 1);
-                    if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sB; tk.cand_i[(size_t)q * tk.cap + slot] = gB; }
+                const bool cA = live && (sA > ts || (sA == ts && gA <= ti));
+                const bool cB = hasB && (sB > ts || (sB == ts && gB <= ti));
+                const unsigned mA = __ballot_sync(RSD_FULL, cA), mB = __ballot_sync(RSD_FULL, cB);
+                if (mA | mB) {
+                    const int lane_id = threadIdx.x & 31;
+                    int base = 0;
+                    if (lane_id == 0) base = atomicAdd(&tk.cand_n[q], __popc(mA) + __popc(mB));
+                    base = __shfl_sync(RSD_FULL, base, 0);
+                    const unsigned below = (1u << lane_id) - 1u;
+                    if (cA) {
+                        const int slot = base + __popc(mA & below);
+                        if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sA; tk.cand_i[(size_t)q * tk.cap + slot] = gA; }
+                    }
+                    if (cB) {
+                        const int slot = base + __popc(mA) + __popc(mB & below);
+                        if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = sB; tk.cand_i[(size_t)q * tk.cap + slot] = gB; }
+                    }
                 }
             }
         }
@@ -198,15 +210,19 @@ __global__ void __launch_bounds__(256) k_topk_fold(TopkState tk) {
     for (int r = tid; r < k; r += 256) { s_bs[r] = tk.best_s[(size_t)q * k + r]; s_bi[r] = tk.best_i[(size_t)q * k + r]; }
     __syncthreads();
     double *cs = tk.cand_s + (size_t)q * tk.cap; int64_t *ci = tk.cand_i + (size_t)q * tk.cap;
-    for (int round = 0; round < k; ++round) {
-        // best remaining candidate (taken ones are marked with index -2)
-        double bs = -2.0; long long bi = 0x7fffffffffffffffLL; int bp = -1;
+    // every thread keeps the best of its own (strided) candidates; after a round only the winner's owner rescans
+    double bs = -2.0; long long bi = 0x7fffffffffffffffLL; int bp = -1;
+    auto rescan = [&]() {
+        bs = -2.0; bi = 0x7fffffffffffffffLL; bp = -1;
         for (int c = tid; c < n; c += 256) {
             const long long idx = ci[c];
-            if (idx == -2) continue;
+            if (idx == -2) continue;                         // taken in an earlier round
             const double s = cs[c];
             if (bp < 0 || key_before(s, idx, bs, bi)) { bs = s; bi = idx; bp = c; }
         }
+    };
+    rescan();
+    for (int round = 0; round < k; ++round) {
         r_s[tid] = bs; r_i[tid] = bi; r_pos[tid] = bp;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
@@ -228,7 +244,6 @@ __global__ void __launch_bounds__(256) k_topk_fold(TopkState tk) {
         __syncthreads();
         if (!better) break;                                  // candidates come out best-first: nothing further can enter
         if (tid == 0) {
-            ci[wp] = -2;
             // duplicates (same global index already in the list) cannot occur: every record is scanned once
             int pos = k - 1;
             while (pos > 0 && (s_bi[pos - 1] < 0 || key_before(ws, wi, s_bs[pos - 1], s_bi[pos - 1]))) {
@@ -236,6 +251,7 @@ __global__ void __launch_bounds__(256) k_topk_fold(TopkState tk) {
             }
             s_bs[pos] = ws; s_bi[pos] = wi;
         }
+        if (tid == (wp & 255)) { ci[wp] = -2; rescan(); }    // the owner of the winner marks it taken and refreshes its best
         __syncthreads();
     }
     __syncthreads();

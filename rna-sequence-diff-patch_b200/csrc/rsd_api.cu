@@ -1340,7 +1340,8 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     RSD_OK_OR_RETURN(upload_costs(mi, st));
 
     // chunking: a small first chunk seeds tau cheaply, then large ones; candidate capacity = chunk size
-    const int64_t CH0 = 4096, CH = (int64_t)1 << 20;
+    // (candidate capacity 2^21 per query: a shard of up to 2 M records — 1/8 of BASELINE config 5 — is one main chunk)
+    const int64_t CH0 = 4096, CH = (int64_t)1 << 21;
     const int QB = fast ? 64 : 16;                           // queries per batch
     const int64_t cap = std::min<int64_t>(std::max<int64_t>(db_n, 1), CH);
     const size_t per_q = (size_t)cap * 16 + (size_t)std::max(k, 1) * 16 + 64;
@@ -1389,7 +1390,7 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
             }
             per_sm = search_per_sm;
             wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
-            if (rest > wave && cap >= wave) main_sz = cap / wave * wave;
+            if (rest > cap && cap >= wave) main_sz = cap / wave * wave;       // a shard that fits one chunk goes in one launch (finer waves below)
         }
         for (int64_t r0 = 0; r0 < db_n;) {
             const bool seed = r0 == 0 && db_n > CH0;
@@ -1402,7 +1403,9 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
                 // costs as much as a full one.  Splitting the query batch over blockIdx.y makes the CTAs shorter and the
                 // waves more numerous (>= 12), so that tail shrinks with them; the selectors are rebuilt per CTA (cheap).
                 unsigned gy = seed ? (unsigned)std::min(nq, 8) : 1u;
-                if (!seed && wave > 0 && nr < 12 * wave) gy = (unsigned)std::min<int64_t>(std::min(nq, 8), (12 * wave + nr - 1) / std::max<int64_t>(nr, 1));
+                int64_t want_waves = 12;              // measured on a 1.25 M-record shard: 12 -> 4.37 ms, 24 -> 4.43, 48 -> 4.64, 96 -> 5.12 (selectors are rebuilt per CTA)
+                if (const char *e = getenv("RSD_SEARCH_WAVES")) want_waves = std::max(atoi(e), 1);
+                if (!seed && wave > 0 && nr < want_waves * wave) gy = (unsigned)std::min<int64_t>(std::min(nq, 16), (want_waves * wave + nr - 1) / std::max<int64_t>(nr, 1));
                 const dim3 grid((unsigned)((threads + 127) / 128), gy);
                 k_search_twin16<<<grid, 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
                                                                                       q_len + q0, nq, tab, tk, alls, db_n, 1u);

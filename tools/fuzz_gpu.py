@@ -160,11 +160,36 @@ def main():
                         b1 = a1[:1].copy()
                 else:
                     b1 = al[rng.integers(0, len(al), size=n2)]
-                res = eng.long_pair(a1, b1, force_mode=force if force != 2 else 0)
+                # second-generation path with random planner knobs: rings, panel width, a memory budget / CTA limit that
+                # forces the row-block x panel-range overflow path, a widened steps field (modular-key wrap regime)
+                knobs = {}
+                if rng.random() < 0.5: knobs["RSD_LONG_C"] = str(rng.choice([4, 8, 16]))
+                if rng.random() < 0.4: knobs["RSD_LONG_BUDGET_MB"] = str(rng.choice([2, 3, 6]))
+                if rng.random() < 0.3: knobs["RSD_LONG_MAXCTAS"] = str(rng.choice([1, 2, 7]))
+                if rng.random() < 0.3: knobs["RSD_LONG_S"] = str(rng.choice([18, 20, 21]))
+                if rng.random() < 0.3: knobs["RSD_LONG_RINGS"] = str(rng.choice([1, 2, 3]))
+                os.environ.update(knobs)
+                try:
+                    fm = force if force != 2 else 0
+                    if rng.random() < 0.5:
+                        res = eng.long_pair(a1, b1, force_mode=fm)
+                        extra = []
+                    else:                                        # a batch: this pair plus two short companions
+                        comp = [(al[rng.integers(0, len(al), size=int(rng.integers(0, 900)))], al[rng.integers(0, len(al), size=int(rng.integers(0, 900)))]) for _ in range(2)]
+                        out = eng.long_pairs([(a1, b1)] + comp, force_mode=fm)
+                        res, extra = out[0], list(zip(out[1:], comp))
+                finally:
+                    for kname in knobs: del os.environ[kname]
                 ops, oi, oj, d = O.canonical_script(O.decode(a1), O.decode(b1), costs)
                 ok = res["dist"] == d and np.array_equal(res["op"], ops) and np.array_equal(res["oi"], oi) and np.array_equal(res["oj"], oj)
+                for r2, (a2, b2) in extra:
+                    if a2.shape[0] == 0 or b2.shape[0] == 0:
+                        ok = ok and r2["op"].shape[0] == a2.shape[0] + b2.shape[0]
+                        continue
+                    o2, i2, j2, d2 = O.canonical_script(O.decode(a2), O.decode(b2), costs)
+                    ok = ok and r2["dist"] == d2 and np.array_equal(r2["op"], o2) and np.array_equal(r2["oi"], i2) and np.array_equal(r2["oj"], j2)
                 cells += float(m) * b1.shape[0]
-                desc = f"long {m}x{b1.shape[0]} mode={eng.last_mode}"
+                desc = f"long {m}x{b1.shape[0]} mode={eng.last_mode} knobs={knobs} batch={len(extra) + 1}"
             else:
                 n = int(rng.choice([1, 50, 3000, 40000]))
                 lens = rng.integers(0 if rng.random() < 0.3 else 20, int(rng.choice([32, 33, 60])), size=n)

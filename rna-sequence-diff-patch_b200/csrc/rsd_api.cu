@@ -1263,6 +1263,61 @@ extern "C" int rsd_db_load(rsd_ctx *c, const uint32_t *words, const int64_t *sta
     std::vector<int64_t> perm((size_t)std::max<int64_t>(n_records, 1)), s_start((size_t)std::max<int64_t>(n_records, 1));
     std::vector<int32_t> s_len((size_t)std::max<int64_t>(n_records, 1));
     for (int64_t i = 0; i < n_records; ++i) perm[(size_t)cnt[(size_t)len[i]]++] = i;
+    // Second key, in front of the length: the record's *tier* = the rank of its rarest symbol when the symbols are ordered
+    // by the number of records that contain them.  A collection of mostly A/G/C/U(+N) records with a few full-IUPAC ones
+    // (second C5 run) then stores the common-alphabet records as a prefix: a search runs the int16x2 kernel
+    // over the longest prefix whose symbols (with the query's) keep every reachable cost dyadic, and only the rest
+    // through the general kernels (search_dev) — instead of the whole database in fp64 because of 1 % of its records.
+    {
+        std::vector<uint16_t> rmask((size_t)std::max<int64_t>(n_records, 1), 0);
+        const int n_thr = n_records >= (1 << 18) ? (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32) : 1;
+        std::atomic<int> bad_rec{0};
+        auto scan = [&](int t) {
+            for (int64_t i = n_records * t / n_thr, i1 = n_records * (t + 1) / n_thr; i < i1; ++i) {
+                const int64_t nw = ((int64_t)len[i] + per - 1) / per;
+                if (start[i] < 0 || start[i] + nw > n_words) { bad_rec.store(1); continue; }
+                uint32_t m = 0;
+                for (int32_t j = 0; j < len[i]; ++j) m |= 1u << ((words[start[i] + j / per] >> ((j % per) * bits)) & ((1u << bits) - 1u));
+                rmask[(size_t)i] = (uint16_t)m;
+            }
+        };
+        if (n_thr == 1) scan(0);
+        else { std::vector<std::thread> pool; for (int t = 0; t < n_thr; ++t) pool.emplace_back(scan, t); for (auto &th : pool) th.join(); }
+        if (bad_rec.load()) return rsd_fail(RSD_EINVAL, "rsd_db_load: a record lies outside the word buffer");
+        int64_t holds[16] = {0};
+        for (int64_t i = 0; i < n_records; ++i) for (int b = 0; b < 16; ++b) holds[b] += (rmask[(size_t)i] >> b) & 1;
+        int order[16];
+        for (int b = 0; b < 16; ++b) order[b] = b;
+        std::stable_sort(order, order + 16, [&](int x, int y) { return holds[x] > holds[y]; });
+        int rank[16];
+        for (int r = 0; r < 16; ++r) rank[order[r]] = r;
+        uint32_t acc_mask = 0;
+        for (int r = 0; r < 16; ++r) { if (holds[order[r]] > 0) acc_mask |= 1u << order[r]; c->db_tier_mask[r] = acc_mask; }
+        std::vector<uint8_t> tier((size_t)std::max<int64_t>(n_records, 1), 0);
+        int64_t tcnt[17] = {0};
+        for (int64_t i = 0; i < n_records; ++i) {
+            int t = 0;
+            for (int b = 0; b < 16; ++b) if ((rmask[(size_t)i] >> b) & 1) t = std::max(t, rank[b]);
+            tier[(size_t)i] = (uint8_t)t; ++tcnt[t + 1];
+        }
+        for (int t = 1; t <= 16; ++t) tcnt[t] += tcnt[t - 1];
+        // The first tiers are merged up to the one that brings the prefix to half of the records: the bulk of the database
+        // (for RNA: everything made of A, G, C, U, whether or not a record happens to lack one of them) is then ONE tier
+        // sorted by length, and the short chunk that seeds the top-k threshold holds typical records (seeding it from
+        // the handful of records that lack a common symbol gave a useless threshold: 8.7 ms in the next fold, ncu).
+        int r0 = 0;
+        while (r0 < 15 && tcnt[r0 + 1] * 2 < n_records) ++r0;
+        if (r0 > 0) {
+            for (int64_t i = 0; i < n_records; ++i) tier[(size_t)i] = (uint8_t)std::max(0, (int)tier[(size_t)i] - r0);
+            for (int t = 0; t + r0 <= 16; ++t) tcnt[t] = t == 0 ? 0 : tcnt[t + r0];
+            for (int t = 16 - r0 + 1; t <= 16; ++t) tcnt[t] = n_records;
+            for (int t = 0; t < 16; ++t) c->db_tier_mask[t] = c->db_tier_mask[std::min(15, t + r0)];
+        }
+        for (int t = 0; t < 16; ++t) c->db_tier_end[t] = tcnt[t + 1];
+        std::vector<int64_t> perm2((size_t)std::max<int64_t>(n_records, 1));
+        for (int64_t r = 0; r < n_records; ++r) { const int64_t i = perm[(size_t)r]; perm2[(size_t)tcnt[tier[(size_t)i]]++] = i; }     // stable: lengths stay sorted inside a tier
+        perm.swap(perm2);
+    }
     std::vector<uint32_t> s_words((size_t)n_words + 8, 0u);
     int64_t w = 0;
     for (int64_t r = 0; r < n_records; ++r) {                       // offsets in stored order (serial, cheap)
@@ -1305,6 +1360,41 @@ extern "C" int rsd_db_free(rsd_ctx *c) {
     return RSD_OK;
 }
 
+// Fast path (int16x2 thread-per-record kernel) applicability, per prefix of the stored order: records [0, db_tier_end[t])
+// use only the symbols db_tier_mask[t] (rsd_db_load).  -> the longest prefix [0, n_fast) whose symbols, together with the
+// queries', keep every reachable cost dyadic and small; its integer tables (mi_fast) and the compact symbol maps
+// (lut = {syms_lo, syms_hi, lut_lo, lut_hi}).
+int rsd_ctx::fast_prefix(uint32_t q_symmask, int64_t max_qlen, int bits, int force_mode, ModeInfo &mi_fast, uint32_t lut[4], int64_t &n_fast) const {
+    n_fast = 0;
+    lut[0] = lut[1] = 0; lut[2] = lut[3] = 0x77777777u;
+    const int QROWS = (int)((max_qlen + 7) / 8 * 8);
+    if (!((force_mode == 0 || force_mode == RSD_MODE_I16X2) && db_maxlen <= 32 && max_qlen >= 1 && QROWS <= 64)) return RSD_OK;
+    for (int t = 0; t < 16; ++t) {
+        if (t > 0 && db_tier_end[t] == db_tier_end[t - 1]) continue;          // no record adds this symbol as its rarest
+        const uint32_t sm = db_tier_mask[t] | q_symmask;
+        ModeInfo m2;
+        RSD_OK_OR_RETURN(classify(sm, max_qlen, db_maxlen, bits, 0, m2));
+        int nsym = 0;
+        bool w8 = true;
+        uint32_t s_lo = 0, s_hi = 0, l_lo = 0x77777777u, l_hi = 0x77777777u;
+        for (int a = 0; a < 16; ++a) if (sm >> a & 1) {
+            if (nsym < 7) {
+                uint64_t s64 = ((uint64_t)s_hi << 32) | s_lo; s64 |= (uint64_t)a << (4 * nsym); s_lo = (uint32_t)s64; s_hi = (uint32_t)(s64 >> 32);
+                uint64_t l64 = ((uint64_t)l_hi << 32) | l_lo; l64 &= ~((uint64_t)15 << (4 * a)); l64 |= (uint64_t)nsym << (4 * a);
+                l_lo = (uint32_t)l64; l_hi = (uint32_t)(l64 >> 32);
+            }
+            ++nsym;
+        }
+        if (m2.dyadic)
+            for (int a = 0; a < 16; ++a) for (int b2 = 0; b2 < 16; ++b2)
+                if ((sm >> a & 1) && (sm >> b2 & 1) && m2.ic.w[a][b2] < -127) w8 = false;
+        if (!(m2.dyadic && m2.i16_ok && w8 && nsym <= 7)) break;
+        mi_fast = m2; n_fast = db_tier_end[t];
+        lut[0] = s_lo; lut[1] = s_hi; lut[2] = l_lo; lut[3] = l_hi;
+    }
+    return RSD_OK;
+}
+
 // queries already on the device; outputs to device buffers (top_idx/top_score [Q][k]) and optionally all scores
 int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len, int64_t n_queries,
                         int64_t max_qlen, int bits, uint32_t q_symmask, int k, int force_mode,
@@ -1314,30 +1404,26 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     if (k < 0 || k > RSD_TOPK_MAX) return rsd_fail(RSD_EINVAL, "rsd_db_search: k must be in 0..%d (ask for all_scores instead)", RSD_TOPK_MAX);
     if (n_queries < 0 || n_queries > 1 << 20) return rsd_fail(RSD_EINVAL, "rsd_db_search: n_queries out of range");
     const uint32_t symmask = db_symmask | q_symmask;
-    ModeInfo mi;
+    ModeInfo mi;                                  // general kernels: every symbol of the database and the queries
     RSD_OK_OR_RETURN(classify(symmask, max_qlen, db_maxlen, bits, force_mode == RSD_MODE_I16X2 ? 0 : force_mode, mi));
     timed = false; last_ms_override = 0.0;
-    // fast path applicability
-    int nsym = 0; uint32_t syms_lo = 0, syms_hi = 0, lut_lo = 0x77777777u, lut_hi = 0x77777777u;
-    bool w8 = true;
-    for (int a = 0; a < 16; ++a) if (symmask >> a & 1) {
-        if (nsym < 7) {
-            if (nsym < 8) { uint64_t s64 = ((uint64_t)syms_hi << 32) | syms_lo; s64 |= (uint64_t)a << (4 * nsym); syms_lo = (uint32_t)s64; syms_hi = (uint32_t)(s64 >> 32); }
-            uint64_t l64 = ((uint64_t)lut_hi << 32) | lut_lo; l64 &= ~((uint64_t)15 << (4 * a)); l64 |= (uint64_t)nsym << (4 * a);
-            lut_lo = (uint32_t)l64; lut_hi = (uint32_t)(l64 >> 32);
-        }
-        ++nsym;
-    }
-    if (mi.dyadic)
-        for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b)
-            if ((symmask >> a & 1) && (symmask >> b & 1) && mi.ic.w[a][b] < -127) w8 = false;
+    // Fast path (int16x2 thread-per-record kernel) applicability, per prefix of the stored order: records [0, db_tier_end[t])
+    // use only the t+1 most common symbols of the database (rsd_db_load).  The longest prefix whose symbols, together with
+    // the queries', keep every reachable cost dyadic and small goes through the fast kernel; the remaining records through
+    // the general kernels in `mi`'s mode.  A database of A/G/C/U(+N) records with a few full-IUPAC ones (non-dyadic 0.66 /
+    // 0.83 under the default table) thus pays fp64 for those few only.
     const int QROWS = (int)((max_qlen + 7) / 8 * 8);
-    const bool fast = mi.dyadic && mi.i16_ok && w8 && nsym <= 7 && db_maxlen <= 32 && max_qlen >= 1 && QROWS <= 64 &&
-                      (force_mode == 0 || force_mode == RSD_MODE_I16X2);
-    if (force_mode == RSD_MODE_I16X2 && !fast) return rsd_fail(RSD_EINVAL, "rsd_db_search: int16x2 search kernel not applicable (symbols, costs or lengths)");
-    if (mode_out) *mode_out = fast ? RSD_MODE_I16X2 : mi.mode;
+    ModeInfo mi_fast{};
+    uint32_t lut4[4] = {0, 0, 0x77777777u, 0x77777777u};
+    int64_t n_fast = 0;
+    RSD_OK_OR_RETURN(fast_prefix(q_symmask, max_qlen, bits, force_mode, mi_fast, lut4, n_fast));
+    const uint32_t syms_lo = lut4[0], syms_hi = lut4[1], lut_lo = lut4[2], lut_hi = lut4[3];
+    const int64_t n_gen = db_n - n_fast;          // records for the general kernels (stored order [n_fast, db_n))
+    if (force_mode == RSD_MODE_I16X2 && n_gen > 0) return rsd_fail(RSD_EINVAL, "rsd_db_search: int16x2 search kernel not applicable (symbols, costs or lengths)");
+    const bool fast = n_fast > 0;
+    if (mode_out) *mode_out = n_gen == 0 ? RSD_MODE_I16X2 : mi.mode;
     if (n_queries == 0) return RSD_OK;
-    RSD_OK_OR_RETURN(upload_costs(mi, st));
+    if (!fast) RSD_OK_OR_RETURN(upload_costs(mi, st));
 
     // chunking: a small first chunk seeds tau cheaply, then large ones; candidate capacity = chunk size
     // (candidate capacity 2^21 per query: a shard of up to 2 M records — 1/8 of BASELINE config 5 — is one main chunk)
@@ -1358,45 +1444,46 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     tk.tau_i = (int64_t *)aux; aux += (size_t)QB * 8;
     tk.cand_n = (int *)aux; aux += (size_t)QB * 4;
     uint2 *rowtab = (uint2 *)db_topi.p;
-    if (!fast) {
-        RSD_OK_OR_RETURN(db_dist.ensure((size_t)cap * 8 + 64));
-        RSD_OK_OR_RETURN(db_tops.ensure((size_t)cap * 12 + 64));
+    const int64_t cap_gen = std::min<int64_t>(std::max<int64_t>(n_gen, 1), cap);
+    if (n_gen > 0) {
+        RSD_OK_OR_RETURN(db_dist.ensure((size_t)cap_gen * 8 + 64));
+        RSD_OK_OR_RETURN(db_tops.ensure((size_t)cap_gen * 12 + 64));
     }
     SearchTab tab{};
-    tab.ins = mi.ic.ins; tab.del = mi.ic.del; tab.inv_scale = 1.0 / (double)(1 << mi.ic.scale_log2);
+    tab.ins = mi_fast.ic.ins; tab.del = mi_fast.ic.del; tab.inv_scale = 1.0 / (double)(1 << mi_fast.ic.scale_log2);
     tab.compact_lut_lo = lut_lo; tab.compact_lut_hi = lut_hi;
     const uint32_t *dbw = (const uint32_t *)db.words.p; const int64_t *dbs = (const int64_t *)db.start.p; const int32_t *dbl = (const int32_t *)db.len.p;
-    if (timing) RSD_CUDA(cudaEventRecord(ev0, st));
+    if (timing && !hold_ev0) RSD_CUDA(cudaEventRecord(ev0, st));        // (the second query group of a host call keeps the first one's start)
     for (int64_t q0 = 0; q0 < n_queries; q0 += QB) {
         const int nq = (int)std::min<int64_t>(QB, n_queries - q0);
         if (k > 0) { k_topk_init<<<(nq + 63) / 64, 64, 0, st>>>(tk, nq); launches += 1; }
+        double *alls = all_scores_dev ? all_scores_dev + (size_t)q0 * db_n : nullptr;
         if (fast) {
+            // the integer tables of the fast prefix (the general part below uploads its own; stream order keeps them apart)
+            RSD_OK_OR_RETURN(upload_costs(mi_fast, st));
             k_build_rowtab<<<(nq * QROWS + 127) / 128, 128, 0, st>>>(q_words, q_start + q0, q_len + q0, nq, bits, QROWS, d_ic, syms_lo, syms_hi, rowtab);
             launches += 1;
-        }
-        // a short first chunk (its queries spread over blockIdx.y) seeds tau; the rest goes in equal chunks <= cap
-        const int64_t rest = std::max<int64_t>(db_n - CH0, 0);
-        const int64_t n_main = (rest + cap - 1) / std::max<int64_t>(cap, 1);
-        int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
-        int64_t wave = 0;
-        if (fast && !getenv("RSD_SEARCH_NOWAVE")) {
-            // the CTAs of a chunk do equal work (the database is sorted by length), so they finish wave by wave: a chunk
-            // that is a whole number of waves (resident CTAs x 256 records) leaves no partly filled last wave
-            int per_sm = 0;
-            const size_t smem_q = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
-            if (search_per_sm_nq != nq || search_per_sm_qrows != QROWS) {
-                RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_twin16, 128, smem_q));
-                search_per_sm = per_sm; search_per_sm_nq = nq; search_per_sm_qrows = QROWS;
+            // a short first chunk (its queries spread over blockIdx.y) seeds tau; the rest goes in equal chunks <= cap
+            const int64_t rest = std::max<int64_t>(n_fast - CH0, 0);
+            const int64_t n_main = (rest + cap - 1) / std::max<int64_t>(cap, 1);
+            int64_t main_sz = n_main ? std::min<int64_t>(cap, ((rest + n_main - 1) / n_main + 255) / 256 * 256) : cap;
+            int64_t wave = 0;
+            if (!getenv("RSD_SEARCH_NOWAVE")) {
+                // the CTAs of a chunk do equal work (the database is sorted by length), so they finish wave by wave: a chunk
+                // that is a whole number of waves (resident CTAs x 256 records) leaves no partly filled last wave
+                int per_sm = 0;
+                const size_t smem_q = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
+                if (search_per_sm_nq != nq || search_per_sm_qrows != QROWS) {
+                    RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_twin16, 128, smem_q));
+                    search_per_sm = per_sm; search_per_sm_nq = nq; search_per_sm_qrows = QROWS;
+                }
+                per_sm = search_per_sm;
+                wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
+                if (rest > cap && cap >= wave) main_sz = cap / wave * wave;       // a shard that fits one chunk goes in one launch (finer waves below)
             }
-            per_sm = search_per_sm;
-            wave = (int64_t)std::max(per_sm, 1) * sm_count * 256;
-            if (rest > cap && cap >= wave) main_sz = cap / wave * wave;       // a shard that fits one chunk goes in one launch (finer waves below)
-        }
-        for (int64_t r0 = 0; r0 < db_n;) {
-            const bool seed = r0 == 0 && db_n > CH0;
-            const int64_t nr = std::min<int64_t>(seed ? CH0 : main_sz, db_n - r0);
-            double *alls = all_scores_dev ? all_scores_dev + (size_t)q0 * db_n : nullptr;
-            if (fast) {
+            for (int64_t r0 = 0; r0 < n_fast;) {
+                const bool seed = r0 == 0 && n_fast > CH0;
+                const int64_t nr = std::min<int64_t>(seed ? CH0 : main_sz, n_fast - r0);
                 const int64_t threads = (nr + 1) / 2;
                 const size_t smem = (size_t)nq * QROWS * 8 + (size_t)nq * 20 + 16;
                 // A chunk of only a few waves (a small shard: 1/8 of the database per GPU) ends in a partly filled wave that
@@ -1410,20 +1497,26 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
                 k_search_twin16<<<grid, 128, smem, st>>>(dbw, dbs, dbl, r0, nr, db_bits, (const int64_t *)db_perm.p, db_base, rowtab, QROWS,
                                                                                       q_len + q0, nq, tab, tk, alls, db_n, 1u);
                 launches += 1;
-            } else {
-                for (int q = 0; q < nq; ++q) {
-                    k_fill_query_view<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(q_start + q0, q_len + q0, q, nr, (int64_t *)db_tops.p,
-                                                                                     (int32_t *)((int64_t *)db_tops.p + cap));
-                    launches += 1;
-                    int mode_unused = 0;
-                    const bool t_save = timing; timing = false;
-                    int rc = distance_dev(q_words, (const int64_t *)db_tops.p, (const int32_t *)((int64_t *)db_tops.p + cap), dbw, dbs + r0,
-                                          dbl + r0, nr, max_qlen, db_maxlen, bits, symmask, force_mode, (double *)db_dist.p, &mode_unused, st);
-                    timing = t_save;
-                    if (rc) return rc;
-                    k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, (const int64_t *)db_perm.p, db_base, q, tk, alls, db_n);
-                    launches += 1;
-                }
+                if (k > 0) { k_topk_fold<<<nq, 256, 0, st>>>(tk); launches += 1; }
+                RSD_CUDA(cudaGetLastError());
+                r0 += nr;
+            }
+        }
+        // records outside the fast prefix (or all of them): one query at a time through the systolic distance kernels
+        for (int64_t r0 = n_fast; r0 < db_n;) {
+            const int64_t nr = std::min<int64_t>(cap_gen, db_n - r0);
+            for (int q = 0; q < nq; ++q) {
+                k_fill_query_view<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(q_start + q0, q_len + q0, q, nr, (int64_t *)db_tops.p,
+                                                                                 (int32_t *)((int64_t *)db_tops.p + cap_gen));
+                launches += 1;
+                int mode_unused = 0;
+                const bool t_save = timing; timing = false;
+                int rc = distance_dev(q_words, (const int64_t *)db_tops.p, (const int32_t *)((int64_t *)db_tops.p + cap_gen), dbw, dbs + r0,
+                                      dbl + r0, nr, max_qlen, db_maxlen, bits, symmask, force_mode == RSD_MODE_I16X2 ? 0 : force_mode, (double *)db_dist.p, &mode_unused, st);
+                timing = t_save;
+                if (rc) return rc;
+                k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, (const int64_t *)db_perm.p, db_base, q, tk, alls, db_n);
+                launches += 1;
             }
             if (k > 0) { k_topk_fold<<<nq, 256, 0, st>>>(tk); launches += 1; }
             RSD_CUDA(cudaGetLastError());
@@ -1465,14 +1558,87 @@ extern "C" int rsd_db_search_topk(rsd_ctx *c, const uint32_t *q_words, const int
     if (all_scores) RSD_OK_OR_RETURN(c->out_f64.ensure(sizeof(double) * (size_t)n_queries * std::max<int64_t>(c->db_n, 1)));
     int64_t max_qlen = 0;
     for (int64_t i = 0; i < n_queries; ++i) max_qlen = std::max<int64_t>(max_qlen, q_len[i]);
-    RSD_OK_OR_RETURN(c->search_dev((const uint32_t *)c->bufQ.words.p, (const int64_t *)c->bufQ.start.p, (const int32_t *)c->bufQ.len.p,
-                                   n_queries, max_qlen, bits, q_symmask, kk, force_mode, (int64_t *)c->s_oi.p, (double *)c->s_oj.p,
-                                   all_scores ? (double *)c->out_f64.p : nullptr, mode_out, st));
-    if (kk > 0) {
-        RSD_CUDA(cudaMemcpyAsync(top_idx, c->s_oi.p, sizeof(int64_t) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
-        RSD_CUDA(cudaMemcpyAsync(top_score, c->s_oj.p, sizeof(double) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
+    // A query that carries a symbol outside the fast kernel's reach (an ambiguity code whose costs are not dyadic) would
+    // send every query of its batch through the general kernels for the whole database.  Queries are therefore grouped:
+    // those that leave a fast prefix first, the others after them, one search per group.
+    std::vector<int64_t> order;
+    int64_t n_first = n_queries;
+    uint32_t mask_first = q_symmask, mask_rest = 0;
+    if (n_queries > 1 && force_mode == 0) {
+        const int per = 32 / bits;
+        std::vector<uint32_t> qm((size_t)n_queries, 0u);
+        for (int64_t q = 0; q < n_queries; ++q) {
+            if (q_start[q] < 0 || q_start[q] + ((int64_t)q_len[q] + per - 1) / per > q_nwords) return rsd_fail(RSD_EINVAL, "rsd_db_search_topk: query %lld lies outside the word buffer", (long long)q);
+            for (int32_t j = 0; j < q_len[q]; ++j) qm[(size_t)q] |= 1u << ((q_words[q_start[q] + j / per] >> ((j % per) * bits)) & ((1u << bits) - 1u));
+        }
+        std::vector<uint32_t> ok_masks, bad_masks;         // masks already classified (few distinct ones)
+        std::vector<char> friendly((size_t)n_queries, 0);
+        for (int64_t q = 0; q < n_queries; ++q) {
+            const uint32_t m = qm[(size_t)q];
+            bool known = false, ok = false;
+            for (uint32_t x : ok_masks) if (x == m) { known = true; ok = true; }
+            for (uint32_t x : bad_masks) if (x == m) known = true;
+            if (!known) {
+                ModeInfo mf; uint32_t l4[4]; int64_t nf = 0;
+                RSD_OK_OR_RETURN(c->fast_prefix(m, max_qlen, bits, 0, mf, l4, nf));
+                ok = nf > 0;
+                (ok ? ok_masks : bad_masks).push_back(m);
+            }
+            friendly[(size_t)q] = ok;
+        }
+        int64_t n_ok = 0;
+        for (int64_t q = 0; q < n_queries; ++q) n_ok += friendly[(size_t)q];
+        // the union of the friendly queries' symbols must itself leave a fast prefix (it does when each one does and the
+        // costs among their symbols are dyadic; checked, not assumed)
+        if (n_ok > 0 && n_ok < n_queries) {
+            uint32_t mu = 0;
+            for (int64_t q = 0; q < n_queries; ++q) if (friendly[(size_t)q]) mu |= qm[(size_t)q];
+            ModeInfo mf; uint32_t l4[4]; int64_t nf = 0;
+            RSD_OK_OR_RETURN(c->fast_prefix(mu, max_qlen, bits, 0, mf, l4, nf));
+            if (nf > 0) {
+                order.reserve((size_t)n_queries);
+                for (int64_t q = 0; q < n_queries; ++q) if (friendly[(size_t)q]) order.push_back(q);
+                for (int64_t q = 0; q < n_queries; ++q) if (!friendly[(size_t)q]) { order.push_back(q); mask_rest |= qm[(size_t)q]; }
+                n_first = n_ok; mask_first = mu;
+            }
+        }
     }
-    if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores, c->out_f64.p, sizeof(double) * (size_t)n_queries * c->db_n, cudaMemcpyDeviceToHost, st));
+    if (!order.empty()) {                             // queries in group order on the device (the words stay where they are)
+        std::vector<int64_t> ps((size_t)n_queries); std::vector<int32_t> pl((size_t)n_queries);
+        for (int64_t r = 0; r < n_queries; ++r) { ps[(size_t)r] = q_start[order[(size_t)r]]; pl[(size_t)r] = q_len[order[(size_t)r]]; }
+        RSD_CUDA(cudaMemcpyAsync(c->bufQ.start.p, ps.data(), sizeof(int64_t) * (size_t)n_queries, cudaMemcpyHostToDevice, st));
+        RSD_CUDA(cudaMemcpyAsync(c->bufQ.len.p, pl.data(), sizeof(int32_t) * (size_t)n_queries, cudaMemcpyHostToDevice, st));
+        RSD_CUDA(cudaStreamSynchronize(st));          // ps / pl are pageable temporaries
+    }
+    int mode_all = 0;
+    for (int g = 0; g < 2; ++g) {
+        const int64_t g0 = g == 0 ? 0 : n_first, g1 = g == 0 ? n_first : n_queries;
+        if (g1 <= g0) continue;
+        int mo = 0;
+        struct Hold { rsd_ctx *c; ~Hold() { c->hold_ev0 = false; } } hold{c};
+        c->hold_ev0 = g == 1 && n_first > 0;
+        RSD_OK_OR_RETURN(c->search_dev((const uint32_t *)c->bufQ.words.p, (const int64_t *)c->bufQ.start.p + g0, (const int32_t *)c->bufQ.len.p + g0,
+                                       g1 - g0, max_qlen, bits, g == 0 ? mask_first : mask_rest, kk, force_mode, (int64_t *)c->s_oi.p + g0 * kk, (double *)c->s_oj.p + g0 * kk,
+                                       all_scores ? (double *)c->out_f64.p + (size_t)g0 * c->db_n : nullptr, &mo, st));
+        mode_all = std::max(mode_all, mo);
+    }
+    if (mode_out) *mode_out = mode_all;
+    if (order.empty()) {
+        if (kk > 0) {
+            RSD_CUDA(cudaMemcpyAsync(top_idx, c->s_oi.p, sizeof(int64_t) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
+            RSD_CUDA(cudaMemcpyAsync(top_score, c->s_oj.p, sizeof(double) * (size_t)n_queries * kk, cudaMemcpyDeviceToHost, st));
+        }
+        if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores, c->out_f64.p, sizeof(double) * (size_t)n_queries * c->db_n, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (int64_t r = 0; r < n_queries; ++r) {       // row r of the device results belongs to query order[r]
+            const int64_t q = order[(size_t)r];
+            if (kk > 0) {
+                RSD_CUDA(cudaMemcpyAsync(top_idx + q * kk, (int64_t *)c->s_oi.p + r * kk, sizeof(int64_t) * (size_t)kk, cudaMemcpyDeviceToHost, st));
+                RSD_CUDA(cudaMemcpyAsync(top_score + q * kk, (double *)c->s_oj.p + r * kk, sizeof(double) * (size_t)kk, cudaMemcpyDeviceToHost, st));
+            }
+            if (all_scores) RSD_CUDA(cudaMemcpyAsync(all_scores + (size_t)q * c->db_n, (double *)c->out_f64.p + (size_t)r * c->db_n, sizeof(double) * (size_t)c->db_n, cudaMemcpyDeviceToHost, st));
+        }
+    }
     RSD_CUDA(cudaStreamSynchronize(st));
     return RSD_OK;
 }

@@ -81,7 +81,7 @@ struct rsd_ctx {
     double last_ms_override = 0.0;
     bool costs_preloaded = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timing = false, timed = false;
+    bool timing = false, timed = false, hold_ev0 = false;
     int64_t launches = 0;
 
     bool have_costs = false;
@@ -110,6 +110,8 @@ struct rsd_ctx {
     int64_t db_n = 0, db_base = 0, db_nwords = 0, db_maxlen = 0;
     int db_bits = 0;
     uint32_t db_symmask = 0;
+    int64_t db_tier_end[16] = {};          // stored records [0, db_tier_end[t]) use only the t+1 most common symbols
+    uint32_t db_tier_mask[16] = {};        // ... whose set is db_tier_mask[t]
     bool db_loaded = false;
     DevBuf db_dist, db_topi, db_tops, db_aux, db_perm;
     int search_per_sm = 0, search_per_sm_nq = -1, search_per_sm_qrows = -1;      // occupancy of the search kernel, asked once per shape
@@ -129,6 +131,7 @@ struct rsd_ctx {
     int distance_dev(const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, const uint32_t *b_words,
                      const int64_t *b_start, const int32_t *b_len, int64_t n_pairs, int64_t max_m, int64_t max_n,
                      int bits, uint32_t symmask, int force_mode, double *d_out, int *mode_out, cudaStream_t st);
+    int fast_prefix(uint32_t q_symmask, int64_t max_qlen, int bits, int force_mode, ModeInfo &mi_fast, uint32_t lut[4], int64_t &n_fast) const;
     int search_dev(const uint32_t *q_words, const int64_t *q_start, const int32_t *q_len, int64_t n_queries,
                    int64_t max_qlen, int bits, uint32_t q_symmask, int k, int force_mode, int64_t *top_idx,
                    double *top_score, double *all_scores_dev, int *mode_out, cudaStream_t st);

@@ -188,3 +188,45 @@ def test_multi_device_search_one_process(R, golden):
             assert np.array_equal(idx3[0], w3[0]) and np.array_equal(sc3[0][:2], w3[1][:2])
         finally:
             me.close()
+
+
+def test_mixed_database_fast_prefix_plus_general_rest(R, eng, golden):
+    """SURVEY 8d, second C5 run: 1 % of the records drawn from all 15 symbols.  The store order puts the A/G/C/U(+N)
+    records first (tiers by rarest symbol, rsd_db_load); the int16x2 kernel scores that prefix, the fp64 kernels the
+    IUPAC records (0.66 / 0.83 are not dyadic) — every score, and the top-k with its collection-order tie-break, must
+    equal the oracle's, also for a query that itself carries an ambiguity code."""
+    rng = np.random.default_rng(515)
+    codes, off = make_db(rng, 30000, iupac_frac=0.01)
+    queries = make_queries(rng, codes, off, 5)
+    q_amb = list(queries[0]); q_amb[3] = "R"; queries.append("".join(q_amb))   # puts every record on the general path for that call
+    costs = golden["default_costs"]
+    eng.set_costs(costs)
+    eng.db_load(R.pack((codes, off), bits=4))
+    try:
+        launches0 = eng.launch_count()
+        idx, sc, alls = eng.db_search_topk(R.pack(queries[:5], bits=4), 10, want_scores=True)
+        n_launch = eng.launch_count() - launches0
+        assert eng.last_mode == 3                       # the mode of the slowest part
+        wi, ws, wa = oracle_topk(queries[:5], codes, off, costs, 10)
+        assert np.array_equal(alls, wa)
+        assert np.array_equal(idx, wi) and np.array_equal(sc, ws)
+        # the fast kernel took the prefix: far fewer launches than 3 per query per chunk over the whole database
+        assert n_launch < 60
+        idx, sc, alls = eng.db_search_topk(R.pack(queries[5:], bits=4), 10, want_scores=True)
+        wi, ws, wa = oracle_topk(queries[5:], codes, off, costs, 10)
+        assert np.array_equal(alls, wa) and np.array_equal(idx, wi) and np.array_equal(sc, ws)
+        # the ambiguous query in the middle of a batch: the library groups the queries (fast-prefix ones first) and
+        # returns the rows in the caller's order
+        mixed = [queries[1], queries[5], queries[0], queries[5], queries[3]]
+        launches0 = eng.launch_count()
+        idx, sc, alls = eng.db_search_topk(R.pack(mixed, bits=4), 10, want_scores=True)
+        assert eng.launch_count() - launches0 < 700    # 2 ambiguous queries x ~100 launches, not 5 x
+        wi, ws, wa = oracle_topk(mixed, codes, off, costs, 10)
+        assert np.array_equal(alls, wa) and np.array_equal(idx, wi) and np.array_equal(sc, ws)
+        # user costs: every symbol pair of this table is dyadic? (A->K 1.5 ...) -> whatever the split, results equal the oracle
+        eng.set_costs(golden["user_costs"])
+        idx, sc, alls = eng.db_search_topk(R.pack(queries[:3], bits=4), 7, want_scores=True)
+        wi, ws, wa = oracle_topk(queries[:3], codes, off, golden["user_costs"], 7)
+        assert np.array_equal(alls, wa) and np.array_equal(idx, wi) and np.array_equal(sc, ws)
+    finally:
+        eng.db_free()

@@ -457,6 +457,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_configs as BC
             e3 = BC.c3(eng, 20000, reps=2); e4 = BC.c4(eng, reps=2); e2i = BC.c2_iupac(eng, 200_000, reps=3)
+            e5i = BC.c5(eng, 2_000_000, nq=64, reps=2, iupac=True)
             extras = {"c3_script_patch_roundtrip": {"pairs": e3["pairs"], "pairs_per_s_device": e3["device_pairs_per_s"],
                                                     "gcups_device": e3["device_gcups"], "pairs_per_s_e2e": e3["e2e_pairs_per_s"],
                                                     "roundtrip_ok": e3["roundtrip_ok"], "oracle_checked_pairs": e3["oracle_checked_pairs"]},
@@ -465,6 +466,9 @@ def main():
                                             "script_equals_oracle_digest": e4["script_equals_oracle_digest"],
                                             "roofline_frac_5ops": e4["device_gcups"] * 5e-3 / peak if peak else None,
                                             "batch": dict(e4["batch"], roofline_frac_5ops=e4["batch"]["device_gcups"] * 5e-3 / peak if peak else None) if e4.get("batch") else None},
+                      "c5_iupac_mixed": dict(e5i, note="C5 second run (SURVEY 8d) at 2*10^6 records: 1 % of the records drawn from all 15 symbols; the int16x2 kernel "
+                                                         "scores the common-alphabet prefix of the stored order, the fp64 kernels the IUPAC records; queries that carry "
+                                                         "non-dyadic symbols form their own group; two queries checked against the oracle on the whole database"),
                       "c2_iupac_fp64": dict(e2i, roofline_frac_dadd=(e2i["device_gcups"] * 5e-3 / peaks["dadd"]) if peaks.get("dadd") else None,
                                             note="15-letter alphabet, default costs.json (0.66 / 0.83 ...): fp64 kernel in the reference's "
                                                  "operation order; 5 fp64-pipe ops per cell (3 DADD + 2 compares) against the measured DADD issue peak")}

@@ -562,14 +562,17 @@ struct SideIn {
 };
 
 // per-block sums of nwords(len) (and of len, for raw codes) for the blocks [b0, b1): sum[b] = words of block b
-static void block_sums(const int32_t *len, int64_t n, int sh, int64_t b0, int64_t b1, int64_t *sum, int64_t *sym_sum) {
+// neg (optional) receives a negative value when one of the lengths is negative (the OR of all of them)
+static void block_sums(const int32_t *len, int64_t n, int sh, int64_t b0, int64_t b1, int64_t *sum, int64_t *sym_sum, std::atomic<int32_t> *neg = nullptr) {
     const int add = (1 << sh) - 1;
+    int32_t any = 0;
     for (int64_t b = b0; b < b1; ++b) {
         const int64_t e = std::min<int64_t>(n, (b + 1) * RSD_SCAN_BLOCK);
         int64_t s = 0, ss = 0;
-        for (int64_t p = b * RSD_SCAN_BLOCK; p < e; ++p) { s += (len[p] + add) >> sh; ss += len[p]; }
+        for (int64_t p = b * RSD_SCAN_BLOCK; p < e; ++p) { s += (len[p] + add) >> sh; ss += len[p]; any |= len[p]; }
         sum[b] = s; if (sym_sum) sym_sum[b] = ss;
     }
+    if (neg && any < 0) neg->store(any);
 }
 // in place: per-block sums -> exclusive prefix, entry nblk = total
 static void block_prefix(int64_t *tab, int64_t nblk) {
@@ -618,6 +621,7 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     int64_t *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [side][0 words, 1 symbols], nblk + 1 entries each
     int64_t nwords[2] = {in[0].nwords, in[1].nwords};
     const size_t tab_bytes = sizeof(int64_t) * 4 * (size_t)(nblk + 1);
+    std::atomic<int32_t> neg_len{0};                    // (declared before the helper threads that write it)
     std::thread helpers[2];
     struct Joiner { std::thread *t; ~Joiner() { for (int s = 0; s < 2; ++s) if (t[s].joinable()) t[s].join(); } } joiner{helpers};
     if (any_canon) {
@@ -635,15 +639,15 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     // a chunk is a contiguous slice of every array.  Pinned host buffers make the copies asynchronous.
     // Packed input: chunk sizes grow geometrically so the first copy is short; the growth stays below the
     // compute/copy time ratio so that no later chunk waits for its data.  Raw codes are four times the bytes and
-    // copy-bound: equal chunks, so that little work is left when the last byte has arrived.
+    // copy-bound: 16 chunks that shrink by 0.85, so that little work is left when the last byte has arrived.
     int n_chunks = 1;
     int64_t bounds[RSD_MAX_CHUNKS + 1];
     bounds[0] = 0;
     if (n_pairs >= (1 << 16)) {
         n_chunks = any_codes ? 16 : 5;
-        double ratio = any_codes ? 1.0 : 1.5;
+        double ratio = any_codes ? 0.85 : 1.5;                 // codes: shrinking chunks, so little compute is left behind the last byte
         if (const char *e = getenv("RSD_CHUNKS")) n_chunks = std::min(std::max(atoi(e), 1), RSD_MAX_CHUNKS);
-        if (const char *e = getenv("RSD_CHUNK_RATIO")) ratio = std::max(atof(e), 1.0);
+        if (const char *e = getenv("RSD_CHUNK_RATIO")) ratio = std::min(std::max(atof(e), 0.5), 4.0);
         double wsum = 0, w = 1.0, acc = 0;
         for (int k = 0; k < n_chunks; ++k) { wsum += w; w *= ratio; }
         w = 1.0;
@@ -711,7 +715,8 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
             const int64_t b0 = p0 / RSD_SCAN_BLOCK, b1 = p1 >= n_pairs ? nblk : p1 / RSD_SCAN_BLOCK;
             for (int s = 0; s < 2; ++s) {
                 if (in[s].canonical()) {
-                    block_sums(in[s].len, n_pairs, sh, b0, b1, tab[s][0], nullptr);
+                    block_sums(in[s].len, n_pairs, sh, b0, b1, tab[s][0], nullptr, &neg_len);
+                    if (neg_len.load() < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: negative length");
                     const int64_t w0 = wacc[s];
                     for (int64_t b = b0; b < b1; ++b) { const int64_t v = tab[s][0][b]; tab[s][0][b] = wacc[s]; wacc[s] += v; }
                     if (wacc[s] > in[s].nwords)
@@ -746,12 +751,35 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
             RSD_OK_OR_RETURN(launch_chunk(k, sk));
         }
     } else {
-        // ---- raw codes: copy-bound, so the copies go out first; block sums of both sides on helper threads ---------
+        // ---- raw codes: copy-bound (1 byte per symbol: 4x the packed bytes), so the copies go out first ------------------
+        // The first chunk's block sums are done here and its codes leave at once; the other blocks are summed on helper
+        // threads meanwhile.  Device buffers are sized by the length bound (n_pairs x longest sequence) so that nothing
+        // has to wait for the totals.
+        const int64_t b_first = n_chunks > 1 ? bounds[1] / RSD_SCAN_BLOCK : nblk;
+        const int per_w = 32 / bits;
+        // (a batch of very uneven lengths would make that bound huge: then the buffers wait for the totals)
+        const bool early = n_chunks > 1 && (double)n_pairs * (double)std::max(max_m, max_n) <= 2147483648.0;
+        for (int s = 0; s < 2; ++s) if (in[s].codes && early) {
+            const int64_t mx = s == 0 ? max_m : max_n;
+            RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)n_pairs * (size_t)mx + 64));
+            RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * ((size_t)n_pairs * (size_t)((mx + per_w - 1) / per_w) + 8)));
+        }
         for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
-            auto job = [&in, &tab, n_pairs, sh, nblk, s] { block_sums(in[s].len, n_pairs, sh, 0, nblk, tab[s][0], in[s].codes ? tab[s][1] : nullptr); };
-            if (n_pairs >= (1 << 17) && !getenv("RSD_NO_HELPERS")) helpers[s] = std::thread(job); else job();
+            auto job = [&in, &tab, &neg_len, n_pairs, sh, nblk, b_first, s] { block_sums(in[s].len, n_pairs, sh, b_first, nblk, tab[s][0], in[s].codes ? tab[s][1] : nullptr, &neg_len); };
+            if (b_first < nblk) { if (n_pairs >= (1 << 17) && !getenv("RSD_NO_HELPERS")) helpers[s] = std::thread(job); else job(); }
+        }
+        int64_t sent0[2] = {0, 0};                       // symbols of chunk 0 already on their way
+        for (int s = 0; s < 2; ++s) if (in[s].canonical()) {
+            block_sums(in[s].len, n_pairs, sh, 0, b_first, tab[s][0], in[s].codes ? tab[s][1] : nullptr, &neg_len);
+            if (neg_len.load() < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: negative length");
+            if (in[s].codes && early) {
+                for (int64_t b = 0; b < b_first; ++b) sent0[s] += tab[s][1][b];
+                if (sent0[s] > (int64_t)n_pairs * (s == 0 ? max_m : max_n)) return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a length exceeds the max length hint");
+                if (sent0[s] > 0) RSD_CUDA(cudaMemcpyAsync(c->raw_codes[s].p, in[s].codes, (size_t)sent0[s], cudaMemcpyHostToDevice, cp));
+            }
         }
         for (int s = 0; s < 2; ++s) if (helpers[s].joinable()) helpers[s].join();
+        if (neg_len.load() < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch: negative length");
         bool whole[2] = {false, false};
         for (int s = 0; s < 2; ++s) {
             if (in[s].canonical()) {
@@ -760,17 +788,21 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
                 if (!in[s].codes && tab[s][0][nblk] > in[s].nwords)
                     return rsd_fail(RSD_EINVAL, "rsd_distance_batch: side %d holds %lld words but its lengths need %lld (canonical layout)", s,
                                     (long long)in[s].nwords, (long long)tab[s][0][nblk]);
+                if (in[s].codes && tab[s][1][nblk] > (int64_t)n_pairs * (s == 0 ? max_m : max_n))
+                    return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: a length exceeds the max length hint");
                 nwords[s] = tab[s][0][nblk];
+                if (in[s].codes) {
+                    if (!early) {
+                        RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
+                        RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
+                    }
+                    RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
+                }
             } else if (n_chunks == 1 || !pair_ordered(in[s].start, in[s].len, 0, n_pairs, n_pairs, in[s].nwords, bits)) whole[s] = true;
         }
         RSD_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, tab_bytes, cudaMemcpyHostToDevice, cp));
         RSD_CUDA(cudaEventRecord(c->ev_tab, cp));
         for (int s = 0; s < 2; ++s) {
-            if (in[s].codes) {
-                RSD_OK_OR_RETURN(dS[s]->words.ensure(sizeof(uint32_t) * (size_t)(nwords[s] + 8)));
-                RSD_OK_OR_RETURN(c->raw_codes[s].ensure((size_t)tab[s][1][nblk] + 64));
-                RSD_OK_OR_RETURN(c->sym_start[s].ensure(sizeof(int64_t) * (size_t)n_pairs));
-            }
             RSD_CUDA(cudaMemsetAsync((uint32_t *)dS[s]->words.p + nwords[s], 0, sizeof(uint32_t) * 8, cp));
             if (whole[s] && nwords[s] > 0) RSD_CUDA(cudaMemcpyAsync(dS[s]->words.p, in[s].words, sizeof(uint32_t) * (size_t)nwords[s], cudaMemcpyHostToDevice, cp));
         }
@@ -784,7 +816,9 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
             if (p1 <= p0) continue;
             for (int s = 0; s < 2; ++s) {
                 if (in[s].codes) {
-                    const int64_t s0 = tab[s][1][p0 / RSD_SCAN_BLOCK], s1 = p1 >= n_pairs ? tab[s][1][nblk] : tab[s][1][p1 / RSD_SCAN_BLOCK];
+                    int64_t s0 = tab[s][1][p0 / RSD_SCAN_BLOCK];
+                    const int64_t s1 = p1 >= n_pairs ? tab[s][1][nblk] : tab[s][1][p1 / RSD_SCAN_BLOCK];
+                    s0 = std::max(s0, sent0[s]);                   // chunk 0 left before the block sums were complete
                     if (s1 > s0) RSD_CUDA(cudaMemcpyAsync((uint8_t *)c->raw_codes[s].p + s0, in[s].codes + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cp));
                     continue;
                 }
@@ -886,7 +920,7 @@ extern "C" int rsd_distance_batch_codes(rsd_ctx *c, const uint8_t *a_codes, cons
     if (bits == 2 && (symmask & ~0xFu)) return rsd_fail(RSD_EINVAL, "rsd: 2-bit packing with symbols outside ACGU");
     RSD_OK_OR_RETURN(c->ensure_device());
     if (n_pairs == 0) return RSD_OK;
-    for (int64_t p = 0; p < n_pairs; ++p) if ((a_len[p] | b_len[p]) < 0) return rsd_fail(RSD_EINVAL, "rsd_distance_batch_codes: negative length at pair %lld", (long long)p);
+    // (negative lengths are caught by the block sums of distance_host: no extra pass over the 8 bytes per pair)
     const SideIn in[2] = {{nullptr, nullptr, a_len, 0, a_codes}, {nullptr, nullptr, b_len, 0, b_codes}};
     return distance_host(c, in, n_pairs, max_m_hint, max_n_hint, bits, symmask, force_mode, out, mode_out);
 }

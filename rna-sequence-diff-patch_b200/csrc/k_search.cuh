@@ -285,6 +285,43 @@ __global__ void k_build_rowtab(const uint32_t *__restrict__ q_words, const int64
     rowtab[idx] = r;
 }
 
+// General path, a whole group of queries at once: pair p = (query q_base + p / n_rec, record rec0 + p % n_rec) as the
+// (start, len) views the systolic distance kernels take.
+__global__ void k_fill_pairs_view(const int64_t *__restrict__ q_start, const int32_t *__restrict__ q_len, int q_base, int n_q,
+                                  const int64_t *__restrict__ db_start, const int32_t *__restrict__ db_len, int64_t rec0, int64_t n_rec,
+                                  int64_t *__restrict__ a_start, int32_t *__restrict__ a_len, int64_t *__restrict__ b_start, int32_t *__restrict__ b_len) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (int64_t)n_q * n_rec) return;
+    const int q = q_base + (int)(p / n_rec); const int64_t r = rec0 + p % n_rec;
+    a_start[p] = q_start[q]; a_len[p] = q_len[q];
+    b_start[p] = db_start[r]; b_len[p] = db_len[r];
+}
+
+// ... and their distances -> scores, optional all_scores rows, candidates (k_score_filter for n_q queries)
+__global__ void k_score_filter_pairs(const double *__restrict__ dist, int64_t rec0, int64_t n_rec, const int64_t *__restrict__ perm,
+                                     int64_t global_base, int q_base, int n_q, TopkState tk, double *__restrict__ all_scores, int64_t all_stride) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (int64_t)n_q * n_rec) return;
+    const int q = q_base + (int)(p / n_rec); const int64_t r = p % n_rec;
+    const double s = __ddiv_rn(1.0, __dadd_rn(1.0, dist[p]));
+    const long long g = perm[rec0 + r];
+    if (all_scores) all_scores[(size_t)q * all_stride + (g - global_base)] = s;
+    if (tk.k > 0) {
+        const double ts = tk.tau_s[q]; const long long ti = tk.tau_i[q];
+        if (s > ts || (s == ts && g <= ti)) {
+            // one atomic per (warp, query): the candidates of a warp almost always belong to one query
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, q);
+            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&tk.cand_n[q], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const int slot = base + __popc(peers & ((1u << lane) - 1u));
+            if (slot < tk.cap) { tk.cand_s[(size_t)q * tk.cap + slot] = s; tk.cand_i[(size_t)q * tk.cap + slot] = g; }
+        }
+    }
+}
+
 __global__ void k_fill_query_view(const int64_t *__restrict__ q_start, const int32_t *__restrict__ q_len, int q,
                                   int64_t n, int64_t *__restrict__ a_start, int32_t *__restrict__ a_len) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

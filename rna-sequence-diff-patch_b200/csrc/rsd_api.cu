@@ -1479,9 +1479,11 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
     tk.cand_n = (int *)aux; aux += (size_t)QB * 4;
     uint2 *rowtab = (uint2 *)db_topi.p;
     const int64_t cap_gen = std::min<int64_t>(std::max<int64_t>(n_gen, 1), cap);
+    const int64_t gen_pairs_max = (int64_t)1 << 23;                          // (query, record) pairs per launch train of the general path
+    const int64_t gen_pairs_cap = std::max<int64_t>(cap_gen, std::min<int64_t>(gen_pairs_max, (int64_t)QB * cap_gen));
     if (n_gen > 0) {
-        RSD_OK_OR_RETURN(db_dist.ensure((size_t)cap_gen * 8 + 64));
-        RSD_OK_OR_RETURN(db_tops.ensure((size_t)cap_gen * 12 + 64));
+        RSD_OK_OR_RETURN(db_dist.ensure((size_t)gen_pairs_cap * 8 + 64));
+        RSD_OK_OR_RETURN(db_tops.ensure((size_t)gen_pairs_cap * 24 + 64));
     }
     SearchTab tab{};
     tab.ins = mi_fast.ic.ins; tab.del = mi_fast.ic.del; tab.inv_scale = 1.0 / (double)(1 << mi_fast.ic.scale_log2);
@@ -1536,20 +1538,28 @@ int rsd_ctx::search_dev(const uint32_t *q_words, const int64_t *q_start, const i
                 r0 += nr;
             }
         }
-        // records outside the fast prefix (or all of them): one query at a time through the systolic distance kernels
+        // records outside the fast prefix (or all of them) through the systolic distance kernels: (query, record) pairs of
+        // several queries per launch train (fill views, plan, distance kernel, score filter), up to PAIRS_MAX pairs at a time
         for (int64_t r0 = n_fast; r0 < db_n;) {
-            const int64_t nr = std::min<int64_t>(cap_gen, db_n - r0);
-            for (int q = 0; q < nq; ++q) {
-                k_fill_query_view<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(q_start + q0, q_len + q0, q, nr, (int64_t *)db_tops.p,
-                                                                                 (int32_t *)((int64_t *)db_tops.p + cap_gen));
+            // without a fast prefix nothing has seeded the thresholds yet: a short first chunk does (every record of an
+            // unseeded 2 M-record chunk was a candidate: 1.4 ms of atomics and a 30 ms fold, ncu)
+            const bool seed_gen = !fast && r0 == 0 && k > 0 && db_n > CH0;
+            const int64_t nr = std::min<int64_t>(seed_gen ? CH0 : cap_gen, db_n - r0);
+            const int qb_max = (int)std::max<int64_t>(1, std::min<int64_t>(nq, gen_pairs_max / std::max<int64_t>(nr, 1)));
+            for (int qa = 0; qa < nq; qa += qb_max) {
+                const int nqb = std::min(qb_max, nq - qa);
+                const int64_t np = (int64_t)nqb * nr;
+                int64_t *va_s = (int64_t *)db_tops.p, *vb_s = va_s + gen_pairs_cap;
+                int32_t *va_l = (int32_t *)(vb_s + gen_pairs_cap), *vb_l = va_l + gen_pairs_cap;
+                k_fill_pairs_view<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(q_start + q0, q_len + q0, qa, nqb, dbs, dbl, r0, nr, va_s, va_l, vb_s, vb_l);
                 launches += 1;
                 int mode_unused = 0;
                 const bool t_save = timing; timing = false;
-                int rc = distance_dev(q_words, (const int64_t *)db_tops.p, (const int32_t *)((int64_t *)db_tops.p + cap_gen), dbw, dbs + r0,
-                                      dbl + r0, nr, max_qlen, db_maxlen, bits, symmask, force_mode == RSD_MODE_I16X2 ? 0 : force_mode, (double *)db_dist.p, &mode_unused, st);
+                int rc = distance_dev(q_words, va_s, va_l, dbw, vb_s, vb_l, np, max_qlen, db_maxlen, bits, symmask,
+                                      force_mode == RSD_MODE_I16X2 ? 0 : force_mode, (double *)db_dist.p, &mode_unused, st);
                 timing = t_save;
                 if (rc) return rc;
-                k_score_filter<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, (const int64_t *)db_perm.p, db_base, q, tk, alls, db_n);
+                k_score_filter_pairs<<<(unsigned)((np + 255) / 256), 256, 0, st>>>((const double *)db_dist.p, r0, nr, (const int64_t *)db_perm.p, db_base, qa, nqb, tk, alls, db_n);
                 launches += 1;
             }
             if (k > 0) { k_topk_fold<<<nq, 256, 0, st>>>(tk); launches += 1; }

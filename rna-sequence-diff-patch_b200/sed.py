@@ -270,10 +270,36 @@ def distance(str1: str, str2: str, costs: dict, engine=None) -> float:
     ca, cb = _validate_and_encode(str1, str2, costs)
     eng = engine or get_engine()
     eng.set_costs(costs)
+    if max(len(ca), len(cb)) >= LONG_PAIR_MIN:                   # one long pair: the panel wavefront uses the whole GPU
+        return float(eng.long_pair(ca, cb, want_script=False)["dist"])
     off_a = np.array([0, len(ca)], np.int64); off_b = np.array([0, len(cb)], np.int64)
     bits = 4 if (ca.size and ca.max() > 3) or (cb.size and cb.max() > 3) else 2
     d = eng.distance_batch(pack((ca, off_a), bits=bits), pack((cb, off_b), bits=bits))
     return float(d[0])
+
+
+LONG_PAIR_MIN = 8192        # from this length on a single pair runs on the panel-wavefront kernels (rsd_long_pair)
+
+
+def edit_script(str1: str, str2: str, costs: dict, engine=None):
+    """generate_es(create_paths(wagnerFisher(str1, str2))[0], str1, str2) (SED:133-334) for a pair of ANY length, without
+    the matrix: the canonical script straight from the device (rsd_script_batch, or rsd_long_pair from LONG_PAIR_MIN
+    symbols on — including pairs whose direction matrix exceeds the device, which run in row blocks).  Empty strings
+    raise IndexError like the reference (SED:278)."""
+    from .encoding import pack
+    if not str1 or not str2:
+        raise IndexError("string index out of range")            # what generate_es does on a border-only path
+    ca, cb = _validate_and_encode(str1, str2, costs)
+    eng = engine or get_engine()
+    eng.set_costs(costs)
+    if max(len(ca), len(cb)) >= LONG_PAIR_MIN:
+        res = eng.long_pair(ca, cb)
+        return es_from_packed(res["op"], res["oi"], res["oj"], str1, str2)
+    bits = 4 if ca.max() > 3 or cb.max() > 3 else 2
+    off_a = np.array([0, len(ca)], np.int64); off_b = np.array([0, len(cb)], np.int64)
+    res = eng.script_batch(pack((ca, off_a), bits=bits), pack((cb, off_b), bits=bits))
+    k = int(res["n_ops"][0])
+    return es_from_packed(res["op"][0, :k], res["oi"][0, :k], res["oj"][0, :k], str1, str2)
 
 
 def _reach_lengths(mask: np.ndarray):

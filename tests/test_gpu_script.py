@@ -159,3 +159,26 @@ def test_roundtrip_property_full_size_lengths(R, eng, golden):
         for o, i, j in zip(res["op"][p, :k], res["oi"][p, :k], res["oj"][p, :k]):
             cost += 1.0 if o != 2 else (0.0 if a[p][i - 1] == b[p][j - 1] else 1.0)
         assert cost == res["dist"][p]
+
+
+def test_edit_script_entry_point_any_length(R, eng, golden, monkeypatch):
+    """sed.edit_script = generate_es(create_paths(wagnerFisher(a, b))[0], a, b) (SED:133-334) without the matrix: the
+    reference's own scripts for short pairs (golden), the oracle's for a pair long enough for the panel-wavefront path,
+    and the same long pair pushed through the row-block overflow path."""
+    from rna_sequence_diff_patch_b200 import sed
+    cases = [c for c in [golden["G1"]] + golden["small"][:40] + list(golden["xml_named"].values()) if "es" in c and c["a"] and c["b"]]
+    for c in cases:
+        costs = golden["user_costs" if c["user"] else "default_costs"]
+        assert sed.edit_script(c["a"], c["b"], costs, engine=eng) == c["es"][0]
+    with pytest.raises(IndexError):
+        sed.edit_script("", "ACGU", golden["default_costs"], engine=eng)
+    rng = np.random.default_rng(99)
+    a = "".join(rng.choice(list("AGCU"), size=9000)); b = "".join(rng.choice(list("AGCU"), size=8700))
+    costs = golden["default_costs"]
+    ops, oi, oj, d = O.canonical_script(a, b, costs)
+    want = sed.es_from_packed(ops, oi, oj, a, b)
+    assert sed.edit_script(a, b, costs, engine=eng) == want
+    assert sed.distance(a, b, costs, engine=eng) == d
+    monkeypatch.setenv("RSD_LONG_BUDGET_MB", "6")
+    assert sed.edit_script(a, b, costs, engine=eng) == want
+    assert sed.patching(want, a) == (0, b)

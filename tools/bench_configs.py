@@ -157,6 +157,34 @@ def c4(eng, L=50000, reps=3, batch_pairs=16):
             "device_gcups": cells / k * 1e-9, "device_s": k}
 
 
+def x2(eng, L=1_000_000):
+    """One pair whose direction matrix (2 bit per cell: 250 GB at 10^6 x 10^6) exceeds the device: the row-block /
+    panel-range overflow path of rsd_long_pair.  No CPU oracle at 10^12 cells: the script is checked as a valid path
+    whose cost equals the reported distance, patch(A) == B, and the distance-only call (no directions, two alternating
+    checkpoint rows) must give the same number."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _synth import c4_pair
+    a, b = c4_pair(seed=20260042, m=L)
+    eng.set_costs(DEFAULT); eng.set_timing(True)
+    os.environ["RSD_TRACE"] = "1"
+    t0 = time.perf_counter(); res = eng.long_pair(a, b); t_first = time.perf_counter() - t0       # includes the one-time cudaMalloc of the pool
+    del os.environ["RSD_TRACE"]
+    t0 = time.perf_counter(); res = eng.long_pair(a, b); t_script = time.perf_counter() - t0; dev_script = eng.last_kernel_ms() * 1e-3
+    t0 = time.perf_counter(); d_only = eng.long_pair(a, b, want_script=False)["dist"]; t_dist = time.perf_counter() - t0; dev_dist = eng.last_kernel_ms() * 1e-3
+    op, oi, oj = res["op"], res["oi"], res["oj"]
+    assert oi[-1] == a.shape[0] and oj[-1] == b.shape[0]
+    di = np.diff(np.concatenate([[0], oi])); dj = np.diff(np.concatenate([[0], oj]))
+    assert np.array_equal(di, (op != 0).astype(np.int64)) and np.array_equal(dj, (op != 1).astype(np.int64)), "not a path"
+    upd = op == 2
+    assert float((op != 2).sum() + (a[oi[upd] - 1] != b[oj[upd] - 1]).sum()) == res["dist"] == d_only, "script cost != distance"
+    assert np.array_equal(b[oj[op != 1] - 1], b), "patching A with the script does not give B"
+    cells = float(a.shape[0]) * b.shape[0]
+    return {"config": "x2-overflow", "m": int(a.shape[0]), "n": int(b.shape[0]), "cells": cells, "dist": res["dist"], "n_ops": int(op.shape[0]),
+            "first_call_wall_s": t_first, "script_wall_s": t_script, "script_device_s": dev_script, "script_gcups_device": cells / dev_script * 1e-9,
+            "distance_only_wall_s": t_dist, "distance_only_device_s": dev_dist, "distance_only_gcups_device": cells / dev_dist * 1e-9,
+            "direction_matrix_bytes": cells / 4, "checked": "valid path, cost == distance == distance-only pass, patch(A) == B"}
+
+
 def c5(eng, n_rec, nq=64, k=10, reps=3, iupac=False):
     rng = np.random.default_rng(20260005)
     lens = rng.integers(24, 32, size=n_rec)
@@ -360,12 +388,14 @@ if __name__ == "__main__":
     ap.add_argument("--c3-pairs", type=int, default=100000)
     ap.add_argument("--c5-records", type=int, default=10_000_000)
     ap.add_argument("--c5-iupac-queries", type=int, default=8)
+    ap.add_argument("--x2-len", type=int, default=1_000_000)
     args = ap.parse_args()
     eng = R.Engine(0)
     for w in args.which.split(","):
         t0 = time.perf_counter()
         res = {"c3": lambda: c3(eng, args.c3_pairs), "c4": lambda: c4(eng), "c5": lambda: c5(eng, args.c5_records),
                "c5i": lambda: c5(eng, args.c5_records, nq=args.c5_iupac_queries, reps=2, iupac=True),
-               "c2i": lambda: c2_iupac(eng, 200_000, reps=2), "c4s": lambda: c4(eng, reps=1, batch_pairs=8)}[w]()
+               "c2i": lambda: c2_iupac(eng, 200_000, reps=2), "c4s": lambda: c4(eng, reps=1, batch_pairs=8),
+               "x2": lambda: x2(eng, args.x2_len)}[w]()
         res["wall_incl_datagen_s"] = time.perf_counter() - t0
         print(json.dumps(res), flush=True)

@@ -457,8 +457,9 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_configs as BC
             e3 = BC.c3(eng, 20000, reps=2); e4 = BC.c4(eng, reps=2); e2i = BC.c2_iupac(eng, 200_000, reps=3)
-            e5i = BC.c5(eng, 2_000_000, nq=64, reps=2, iupac=True)
-            extras = {"c3_script_patch_roundtrip": {"pairs": e3["pairs"], "pairs_per_s_device": e3["device_pairs_per_s"],
+            e5i = BC.c5(eng, 2_000_000, nq=64, reps=2, iupac=True); e1 = BC.c1(eng)
+            extras = {"c1_xml_pairs_dropin_surface": e1,
+                      "c3_script_patch_roundtrip": {"pairs": e3["pairs"], "pairs_per_s_device": e3["device_pairs_per_s"],
                                                     "gcups_device": e3["device_gcups"], "pairs_per_s_e2e": e3["e2e_pairs_per_s"],
                                                     "roundtrip_ok": e3["roundtrip_ok"], "oracle_checked_pairs": e3["oracle_checked_pairs"]},
                       "c4_long_pair_50kb": {"gcups_device": e4["device_gcups"], "ms_device": e4["device_s"] * 1e3,

@@ -333,6 +333,9 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         }
         c->long_fwd_ms = fwd_ms_total;
     }
+    // a pool of tens of GB (one huge pair) is not kept: the next call of any kind finds the memory free again; the pool
+    // of an ordinary batch stays (cudaMalloc of 13 GB costs more than the batch itself)
+    if (c->long_pool.cap > ((size_t)32 << 30)) { RSD_CUDA(cudaStreamSynchronize(st)); c->long_pool.release(); }
     // ---- pairs that need the exact-double / fp64 kernels ----
     for (int p : fallback) {
         int mo = 0;

@@ -157,6 +157,29 @@ def c4(eng, L=50000, reps=3, batch_pairs=16):
             "device_gcups": cells / k * 1e-9, "device_s": k}
 
 
+def c1(eng):
+    """BASELINE config 1: the named test_input.xml pairs through the StringEditDistance surface (wagnerFisher ->
+    create_paths -> generate_es -> patching, and the reverse script), compared with what the unmodified reference
+    returned for them (tests/golden/ref_golden.json: G2-G5 of SURVEY Appendix B); wall time per pair."""
+    from rna_sequence_diff_patch_b200 import sed
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_golden.json")))
+    times = []
+    for name, c in g["xml_named"].items():
+        costs = g["user_costs" if c["user"] else "default_costs"]
+        t0 = time.perf_counter()
+        dp = sed.wagner_fisher(c["a"], c["b"], costs, engine=eng)
+        paths = sed.create_paths(dp)
+        es = sed.generate_es(paths[0], c["a"], c["b"])
+        code, out = sed.patching(es, c["a"])
+        rcode, back = sed.patching(sed.generate_rev_es(es), c["b"])
+        times.append(time.perf_counter() - t0)
+        assert dp[len(dp) - 1][len(dp[0]) - 1].value == c["distance"] and len(paths) == c["n_paths"], name
+        assert es == c["es"][0] and [code, out] == c["patch0"] and [rcode, back] == c["rev_patch0"], name
+        assert sed.edit_script(c["a"], c["b"], costs, engine=eng) == es
+    return {"config": "C1", "pairs": len(times), "ms_per_pair_all_steps": float(np.mean(times[1:]) * 1e3) if len(times) > 1 else float(times[0] * 1e3),
+            "checked": "distance, number of co-optimal paths, ES of paths[0], patch and reverse-patch results == the reference's (golden)"}
+
+
 def x2(eng, L=1_000_000):
     """One pair whose direction matrix (2 bit per cell: 250 GB at 10^6 x 10^6) exceeds the device: the row-block /
     panel-range overflow path of rsd_long_pair.  No CPU oracle at 10^12 cells: the script is checked as a valid path
@@ -396,6 +419,6 @@ if __name__ == "__main__":
         res = {"c3": lambda: c3(eng, args.c3_pairs), "c4": lambda: c4(eng), "c5": lambda: c5(eng, args.c5_records),
                "c5i": lambda: c5(eng, args.c5_records, nq=args.c5_iupac_queries, reps=2, iupac=True),
                "c2i": lambda: c2_iupac(eng, 200_000, reps=2), "c4s": lambda: c4(eng, reps=1, batch_pairs=8),
-               "x2": lambda: x2(eng, args.x2_len)}[w]()
+               "x2": lambda: x2(eng, args.x2_len), "c1": lambda: c1(eng)}[w]()
         res["wall_incl_datagen_s"] = time.perf_counter() - t0
         print(json.dumps(res), flush=True)

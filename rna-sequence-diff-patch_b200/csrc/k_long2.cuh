@@ -42,7 +42,15 @@ struct LongLaunch2 {
 };
 
 // One panel of one job: rows r0 .. r1-1 of the 32*C columns of panel w.  Same arithmetic as k_long_fwd32x2.
-template <int C, bool DIRS>
+//
+// REL: keys are held *relative to a per-lane base* (a lane's keys, and those its left neighbour hands over, lie within
+// (C + 34) border steps of each other — the host checks that this stays below 2^30), so they can be compared as plain
+// signed integers instead of through wrapped differences: min(left, up, diag + w) is one VIMNMX3 (distance only) or two
+// VIMNMX with the two differences for the direction bits, and the chain from a cell to its right neighbour is one
+// instruction instead of VIADDMNMX + IADD — what a lone warp per scheduler waits on.  The base moves to the lane's
+// first column at every block start; values cross lanes with the difference of the two bases added, and everything
+// written to memory (boundary columns, checkpoint rows) is the absolute key modulo 2^32 as before.
+template <int C, bool DIRS, bool REL>
 __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, const int lane, const IntCosts *__restrict__ icp,
                                             uint32_t *s_w, uint32_t *s_pub, uint8_t *s_a) {
     __syncwarp();
@@ -62,8 +70,15 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         const int bc = (col0 + c < n) ? __ldg(J.b + col0 + c) : 0;
         H[c] = J.top ? __ldcg(J.top + col0 + c) : 0u; acc[c] = 0u; bca[c] = sbase + 4u * (uint32_t)bc;
     }
-    uint32_t last0 = 0u, last1 = H[C - 1];
     uint32_t prev_recv1 = (J.top && col0 > 0) ? __ldcg(J.top + col0 - 1) : 0u;       // key of (row r0, the column left of this strip)
+    uint32_t base = 0u, d_nb = 0u;                     // REL: this lane's base; left neighbour's base minus this one
+    if constexpr (REL) {
+        base = H[0];
+#pragma unroll
+        for (int c = 0; c < C; ++c) H[c] -= base;
+        prev_recv1 -= base;
+    }
+    uint32_t last0 = 0u, last1 = H[C - 1];
     long long full = 0;
     const unsigned long long *bin = w > 0 ? J.bound + (size_t)(w - 1) * J.bstride : nullptr;
     unsigned long long *bout = J.bound + (size_t)w * J.bstride;
@@ -76,6 +91,14 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
 
 #pragma unroll 1
     for (int t0 = 0; t0 < steps; t0 += 16) {
+        if constexpr (REL) {                           // rebase: every key this lane holds moves with its first column
+            const uint32_t delta = H[0];
+            base += delta;
+#pragma unroll
+            for (int c = 0; c < C; ++c) H[c] -= delta;
+            last0 -= delta; last1 -= delta; prev_recv1 -= delta;
+            d_nb = __shfl_up_sync(RSD_FULL, base, 1) - base;
+        }
         const uint32_t last_at_block_start = last1;
         if (publish) {
             const int r = 2 * (t0 - 47) + lane;
@@ -125,6 +148,54 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0[c]) : "r"(bca[c] + off0));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[c]) : "r"(bca[c] + off1));
             }
+            uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
+            uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
+            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, 2 * k), b1 = __shfl_sync(RSD_FULL, bval, 2 * k + 1);
+            if constexpr (REL) { recv0 += d_nb; recv1 += d_nb; }
+            if (lane == 0) { recv0 = (w > 0 ? b0 : 0u) - base; recv1 = (w > 0 ? b1 : 0u) - base; }       // (base == 0 unless REL)
+            if constexpr (REL) {
+                if (on0) {
+                    int left = (int)recv0, diag = (int)prev_recv1, h0[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int up = (int)H[c];
+                        const int x = diag + (int)w0[c];
+                        if constexpr (DIRS) {
+                            const int t2 = min(up, x);                        // ties keep DEL
+                            acc[c] = __funnelshift_l((uint32_t)(t2 - left), acc[c], 1);      // "not INS" (ties keep INS)
+                            acc[c] = __funnelshift_l((uint32_t)(x - up), acc[c], 1);         // then "UPD rather than DEL"
+                            h0[c] = min(left, t2);
+                        } else h0[c] = __vimin3_s32(x, up, left);
+                        diag = up; left = h0[c];
+                    }
+                    last0 = (uint32_t)left;
+                    if (on1) {
+                        int diag1 = (int)recv0, left1 = (int)recv1;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const int up = h0[c];
+                            const int x = diag1 + (int)w1[c];
+                            int hn;
+                            if constexpr (DIRS) {
+                                const int t2 = min(up, x);
+                                acc[c] = __funnelshift_l((uint32_t)(t2 - left1), acc[c], 1);
+                                acc[c] = __funnelshift_l((uint32_t)(x - up), acc[c], 1);
+                                hn = min(left1, t2);
+                            } else hn = __vimin3_s32(x, up, left1);
+                            diag1 = up; H[c] = (uint32_t)hn; left1 = hn;
+                        }
+                        last1 = (uint32_t)left1;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) { H[c] = (uint32_t)h0[c]; if constexpr (DIRS) acc[c] <<= 2; }
+                        last1 = last0;
+                    }
+                    prev_recv1 = recv1;
+                } else if constexpr (DIRS && !STEADY) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] <<= 4;
+                }
+            } else {
             uint32_t t2a[C]; int e1a[C];
             {
                 uint32_t diag = prev_recv1;
@@ -137,10 +208,6 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
                     diag = up;
                 }
             }
-            uint32_t recv0 = __shfl_up_sync(RSD_FULL, last0, 1);
-            uint32_t recv1 = __shfl_up_sync(RSD_FULL, last1, 1);
-            const uint32_t b0 = __shfl_sync(RSD_FULL, bval, 2 * k), b1 = __shfl_sync(RSD_FULL, bval, 2 * k + 1);
-            if (lane == 0) { recv0 = w > 0 ? b0 : 0u; recv1 = w > 0 ? b1 : 0u; }
             if (on0) {
                 uint32_t left = recv0, h0[C];
 #pragma unroll
@@ -181,7 +248,8 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc[c] <<= 4;
             }
-            if (lane == 31) { s_pub[2 * k] = last0; s_pub[2 * k + 1] = last1; }
+            }
+            if (lane == 31) { s_pub[2 * k] = last0 + base; s_pub[2 * k + 1] = last1 + base; }      // absolute keys (base == 0 unless REL)
         }
         if constexpr (DIRS) {
             // the 16 rows of the last 8 steps, all lanes at once: 32 * C consecutive words of group (t0 + k8) / 8
@@ -197,7 +265,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     }
     if (J.bottom) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) __stcg(J.bottom + col0 + c, H[c]);
+        for (int c = 0; c < C; ++c) __stcg(J.bottom + col0 + c, H[c] + base);
     }
     if (strip_on && col0 <= n - 1 && n - 1 < col0 + C) {
         // `full` follows column C-1 of this lane from row r0 to row r1; keyacc holds the exact key of that column at row r0
@@ -215,7 +283,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     }
 }
 
-template <int C, bool DIRS>
+template <int C, bool DIRS, bool REL>
 __global__ void __launch_bounds__(32)
 k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
     __shared__ uint32_t s_w[320];
@@ -227,7 +295,7 @@ k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
     const int wl = (int)blockIdx.x - L.ring_cta0[g];
     for (int j = L.ring_job0[g]; j < L.ring_job0[g + 1]; ++j) {
         const LongJob2 J = L.jobs[j];
-        if (wl < J.w_cnt) long2_panel<C, DIRS>(J, J.w_lo + wl, lane, icp, s_w, s_pub, s_a);
+        if (wl < J.w_cnt) long2_panel<C, DIRS, REL>(J, J.w_lo + wl, lane, icp, s_w, s_pub, s_a);
     }
 }
 

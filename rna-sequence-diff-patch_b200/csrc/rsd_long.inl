@@ -67,6 +67,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     std::vector<LongPairPlan> P((size_t)n_pairs);
     std::vector<int> fallback;                       // pairs for rsd_long_pair (fp64 / exact-double keys)
     ModeInfo mi_up{}; bool have_mi = false;
+    long long maxc_all = 0;                          // largest |scaled cost| among the symbols of the call
     // one set of integer cost tables for the whole call: classified on the union of the symbols of every pair
     uint32_t symmask = 0; int64_t max_m = 0, max_n = 0;
     for (int p = 0; p < n_pairs; ++p) {
@@ -81,17 +82,22 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         for (int64_t j = 0; j < Q.n; ++j) { if (b[p][j] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15"); sm |= 1u << b[p][j]; }
         symmask |= sm; max_m = std::max(max_m, Q.m); max_n = std::max(max_n, Q.n);
     }
-    // Rings and panel width.  Measured on 50 kb pairs (tools/dbg_long_batch.py, profiles/r02_long_batch.log): one ring per
-    // pair (up to 16) beats fewer, longer rings; throughput peaks at 1500-2000 warps in flight (2.5-3.5 per SM scheduler),
-    // and a lone warp's step time hardly grows from 4 to 8 columns per lane (it is latency-bound), so 8 columns per lane
-    // unless that puts more than ~2000 warps in flight, then 16 (K = 8: 1.56 TCUPS at 8, K = 12: 2.17 TCUPS at 16).
+    // Rings and panel width, from measurements on 50 kb pairs (tools/dbg_long_batch.py, profiles/r02_long_batch_sweep.log):
+    // a round of r pairs side by side (one ring each, 16 columns per lane) takes 7.6 / 11.3 / 11.0 / 16.5 ms for
+    // r = 4 / 8 / 12 / 16, i.e. 1.9 / 1.4 / 0.92 / 1.03 ms per pair: about 1200 warps in flight (2 per SM scheduler) is
+    // the sweet spot, more only adds contention.  So: r* = 1200 / (panels of a pair at 16 columns per lane) rings when
+    // the batch has pairs for at least two rounds of them, else one ring per pair (up to 16: a second round would cost
+    // more than the contention); 16 columns per lane once ~700 warps are in flight at 8, else 8 (a lone warp's step
+    // hardly grows from 4 to 8 columns, so 4 never wins).
     int rings_want = 16;
     {
         int nk = 0; double sum_n = 0;
         for (int p = 0; p < n_pairs; ++p) if (!P[p].trivial) { ++nk; sum_n += (double)P[p].n; }
+        const double avg_n = nk ? sum_n / nk : 0.0;
+        const int r_star = (int)std::min(16.0, std::max(1.0, std::floor(1200.0 / std::max(1.0, avg_n / 512.0) + 0.5)));
+        rings_want = nk <= std::min(16, r_star + 4) ? std::max(nk, 1) : r_star;
         if (const char *e = getenv("RSD_LONG_RINGS")) rings_want = std::min(std::max(atoi(e), 1), RSD_LONG2_MAX_RINGS);
-        const double warps8 = nk ? (double)std::min(nk, rings_want) * (sum_n / nk) / 256.0 : 0.0;
-        C = warps8 > 2000.0 ? 16 : 8;
+        C = (double)std::min(nk, rings_want) * (avg_n / 256.0) >= 700.0 ? 16 : 8;
         if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) C = v; }
     }
     if (symmask) {
@@ -101,6 +107,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         long long maxc = std::max<long long>(mi.ic.ins, mi.ic.del);
         for (int x = 0; x < 16; ++x) for (int y = 0; y < 16; ++y)
             if ((symmask >> x & 1) && (symmask >> y & 1)) maxc = std::max<long long>(maxc, std::llabs((long long)mi.ic.w[x][y]));
+        maxc_all = maxc;
         for (int p = 0; p < n_pairs; ++p) {
             LongPairPlan &Q = P[p];
             if (Q.trivial) continue;
@@ -133,8 +140,15 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     }
     if (have_mi) {
         RSD_OK_OR_RETURN(c->upload_costs(mi_up, st));
-        const void *kfn_d = C == 4 ? (const void *)k_long2<4, true> : C == 8 ? (const void *)k_long2<8, true> : (const void *)k_long2<16, true>;
-        const void *kfn_n = C == 4 ? (const void *)k_long2<4, false> : C == 8 ? (const void *)k_long2<8, false> : (const void *)k_long2<16, false>;
+        // relative keys (plain signed compares) when every pair's keys stay within 2^30 of their lane's base: (C + 40)
+        // border steps of at most maxc << S each — implied by the eligibility bound above for C <= 16, checked anyway;
+        // RSD_LONG_NOREL keeps the wrapped-difference kernels under test
+        bool rel = !getenv("RSD_LONG_NOREL");
+        for (int p = 0; p < n_pairs; ++p) if (P[p].eligible && (((long long)(C + 40) * maxc_all) << P[p].S) >= (1ll << 30)) rel = false;
+        const void *kfn_d = rel ? (C == 4 ? (const void *)k_long2<4, true, true> : C == 8 ? (const void *)k_long2<8, true, true> : (const void *)k_long2<16, true, true>)
+                                : (C == 4 ? (const void *)k_long2<4, true, false> : C == 8 ? (const void *)k_long2<8, true, false> : (const void *)k_long2<16, true, false>);
+        const void *kfn_n = rel ? (C == 4 ? (const void *)k_long2<4, false, true> : C == 8 ? (const void *)k_long2<8, false, true> : (const void *)k_long2<16, false, true>)
+                                : (C == 4 ? (const void *)k_long2<4, false, false> : C == 8 ? (const void *)k_long2<8, false, false> : (const void *)k_long2<16, false, false>);
         int per_sm = 0;
         RSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn_d, 32, 0));
         int64_t max_ctas = (int64_t)per_sm * c->sm_count;

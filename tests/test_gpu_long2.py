@@ -148,3 +148,21 @@ def test_overflow_path_equals_one_launch_at_60kb(R, eng, golden, monkeypatch):
         assert eng.long_pair(a, b, want_script=False)["dist"] == ref["dist"]
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_wrapped_difference_kernels_stay_under_test(R, eng, golden, monkeypatch):
+    """The default kernels hold keys relative to a per-lane base (plain signed compares); the wrapped-difference kernels
+    they replace remain the path for wide keys (RSD_LONG_NOREL forces them): batch, overflow blocks and the wrap regime."""
+    monkeypatch.setenv("RSD_LONG_NOREL", "1")
+    pairs = make_pairs(404, SHAPES[:6])
+    for costs in (golden["default_costs"], golden["user_costs"]):
+        eng.set_costs(costs)
+        for r, (a, b) in zip(eng.long_pairs(pairs), pairs):
+            check(r, a, b, costs)
+    monkeypatch.setenv("RSD_LONG_BUDGET_MB", "2")
+    monkeypatch.setenv("RSD_LONG_S", "21")           # user costs: still inside the 32-bit bound, absolute keys wrap
+    a, b = pairs[0]
+    res = eng.long_pair(a, b)
+    assert res["mode"] == 2
+    check(res, a, b, costs)
+    check(eng.long_pair(a, b, want_script=False), a, b, costs, script=False)

@@ -102,7 +102,7 @@ def c3(eng, n_pairs, reps=3):
             "roundtrip_ok": bool(ok.all()), "oracle_checked_pairs": int(sample.shape[0]), "output": "op bytes + n_ops + dist + ok (oi/oj derivable by prefix sum), pinned host buffers"}
 
 
-def c4(eng, L=50000, reps=3, batch_pairs=16):
+def c4(eng, L=50000, reps=3, batch_pairs=24):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _synth import c4_pair                      # the pair whose oracle script digest is committed (tests/golden/c4_digest.json)
     a, b = c4_pair(m=L)

@@ -8,7 +8,7 @@ from rna_sequence_diff_patch_b200 import cost_tables
 from _synth import c4_pair
 import torch
 L = int(os.environ.get("L", 50000))
-pairs = [c4_pair(seed=20260004 + k, m=L) for k in range(16)]
+pairs = [c4_pair(seed=20260004 + k, m=L) for k in range(int(os.environ.get("NPAIRS", 16)))]
 eng = R.Engine(0); eng.set_costs(cost_tables.default_costs()); eng.set_timing(True)
 single = eng.long_pair(*pairs[0])
 os.environ["RSD_LONG_V1"] = "1"

@@ -255,6 +255,18 @@ def test_shared_sequence_layout_falls_back_to_whole_copy(R, eng, golden):
         _lib.ptr(Br.words, C.c_uint32), _lib.ptr(b_start, C.c_int64), _lib.ptr(b_len, C.c_int32), Br.words.shape[0],
         n, len(q), 40, 2, 0xF, 0, _lib.ptr(out2, C.c_double), C.byref(mode)))
     assert np.array_equal(out2, want)
+    # in pair order for the first chunks, out of order only from pair 50 000 on (the tail stored reversed): the chunks
+    # already sent stay valid, the whole buffer follows for the rest
+    order3 = np.concatenate([np.arange(50000), np.arange(50000, n)[::-1]])
+    Bt = R.pack([b[k] for k in order3])
+    inv = np.empty(n, np.int64); inv[order3] = np.arange(n)
+    b_start3 = Bt.start[inv].copy(); b_len3 = Bt.len[inv].copy()
+    out3 = np.zeros(n)
+    _lib.check(R.load_library().rsd_distance_batch(
+        eng.ctx, _lib.ptr(A.words, C.c_uint32), None, _lib.ptr(A.len, C.c_int32), A.words.shape[0],
+        _lib.ptr(Bt.words, C.c_uint32), _lib.ptr(b_start3, C.c_int64), _lib.ptr(b_len3, C.c_int32), Bt.words.shape[0],
+        n, len(q), 40, 2, 0xF, 0, _lib.ptr(out3, C.c_double), C.byref(mode)))
+    assert np.array_equal(out3, want)
 
 
 def test_canonical_layout_without_start_equals_explicit_start(R, eng, golden):

@@ -311,36 +311,43 @@ struct LongTb2 {
 };
 
 __global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restrict__ jobs) {
-    constexpr int TR = 16, TC = 256;
-    __shared__ uint32_t tile[TR][TC];
+    // 32 groups (512 skewed row positions: the rows i-449 .. i of every column) x 384 columns = 48 KB of direction words,
+    // brought in with cp.async (16 bytes per request, all of a tile in flight together, no staging registers): one
+    // memory round trip per ~384 path steps.  (16 x 256 tiles through registers: 1.33 ms per 50 kb pair, of which
+    // ~80 % was waiting for the 258 tile loads.)
+    constexpr int TR = 32, TC = 384;
+    __shared__ __align__(16) uint32_t tile[TR][TC];
     const LongTb2 J = jobs[blockIdx.x];
     const int lane = threadIdx.x;
     int i = J.state[0], j = J.state[1], pos = J.state[2];
     if (i < 0) { i = J.m; j = J.n; pos = J.m + J.n; }
     const int r0 = J.r0, n_pad = J.n_pad;
-    const int C = J.C;
+    const int logC = J.C == 4 ? 2 : J.C == 8 ? 3 : 4;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
     while (i > r0 && j > 0) {
         // groups that hold the rows <= i of every column of the tile: row r of a column of lane l sits at position r + 2 l
         const int rb_hi = (i - 1 - r0 + 62) >> 4, rb_lo = max(rb_hi - TR + 1, 0);
-        const int c_hi = j - 1, c_lo = max(c_hi - TC + 1, 0);
-        const int nr = rb_hi - rb_lo + 1, nc = c_hi - c_lo + 1;
-        {
-            uint32_t v[TR * (TC / 32)];
+        // columns: a 16-byte aligned window that ends at or just after column j-1 (n_pad is a multiple of 128)
+        const int c_lo = max(((j - 1) | 3) - (TC - 1), 0);
+        const int nr = rb_hi - rb_lo + 1, nc4 = min(TC, n_pad - c_lo) >> 2;       // 16-byte pieces per row inside the matrix
+        for (int r = 0; r < nr; ++r) {
+            const uint32_t *src = J.dirs + (size_t)(rb_lo + r) * n_pad + c_lo;
 #pragma unroll
-            for (int q = 0; q < TR * (TC / 32); ++q) {
-                const int r = q / (TC / 32), c = lane + 32 * (q % (TC / 32));
-                v[q] = (r < nr && c < nc) ? __ldg(J.dirs + (size_t)(rb_lo + r) * n_pad + c_lo + c) : 0u;
+            for (int q = 0; q < TC / 4 / 32; ++q) {
+                const int c4 = lane + 32 * q;
+                if (c4 < nc4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (uint32_t)((r * TC + 4 * c4) * 4)), "l"(src + 4 * c4) : "memory");
             }
-#pragma unroll
-            for (int q = 0; q < TR * (TC / 32); ++q) tile[q / (TC / 32)][lane + 32 * (q % (TC / 32))] = v[q];
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         const int i_min = r0 + rb_lo * 16;               // rows above this (block-relative >= 16 rb_lo) are inside the tile for every lane
         while (i > i_min && j > c_lo) {
             const int ii = i - lane, jj = j - lane;
             uint32_t code = 3u;
             if (ii > i_min && jj > c_lo) {
-                const int pos16 = (ii - 1 - r0) + 2 * (((jj - 1) / C) & 31);
+                const int pos16 = (ii - 1 - r0) + 2 * (((jj - 1) >> logC) & 31);
                 code = dir_decode(tile[(pos16 >> 4) - rb_lo][(jj - 1) - c_lo], pos16);
             }
             const unsigned diag_mask = __ballot_sync(RSD_FULL, code == 2u);

@@ -23,8 +23,10 @@ struct LongJob2 {
                                    // the word (g, column) of a column held by lane l holds the block rows 16 g - 2 l .. + 15,
                                    // i.e. what the lane computed in the steps 8 g .. 8 g + 7 — so a whole warp stores its
                                    // words at the same step, 32 * C * 4 contiguous bytes, with no per-row test
-    unsigned long long *bound;     // [n_panels][bstride] right-most column of every panel, rows r0 .. r1-1, sentinel-preset
+    unsigned long long *bound;     // [n_panels][bstride] right-most column of every panel, rows r0 .. r1-1: (gen << 32 | key)
     int bstride;
+    unsigned gen;                  // generation tag of this launch group: a boundary word is ready when its high half equals it
+                                   // (no per-call memset of the array: stale words carry older tags, a fresh pool is zeroed once)
     long long *keyacc;             // exact key of the pair's last column, carried from row block to row block
     double *dist;                  // written by the launch with r1 == m
     int S;
@@ -83,6 +85,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     const unsigned long long *bin = w > 0 ? J.bound + (size_t)(w - 1) * J.bstride : nullptr;
     unsigned long long *bout = J.bound + (size_t)w * J.bstride;
     const bool publish = (w + 1 < J.n_panels);
+    const unsigned gen = J.gen;
     uint32_t *dcol = DIRS ? J.dirs + col0 : nullptr;
     const int steps = (rows + 1) / 2 + 31 + 16;       // + one block so the last rows get published
     auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? __ldg(arow + r) : (uint8_t)0; };
@@ -102,7 +105,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         const uint32_t last_at_block_start = last1;
         if (publish) {
             const int r = 2 * (t0 - 47) + lane;
-            if (r >= 0 && r < rows) st_cg_u64(bout + r, (1ull << 32) | (unsigned long long)s_pub[lane]);
+            if (r >= 0 && r < rows) st_cg_u64(bout + r, ((unsigned long long)gen << 32) | (unsigned long long)s_pub[lane]);
         }
         __syncwarp();
         // The 32 boundary rows of this block were requested one block ahead (raw_next): once the panel runs far enough
@@ -112,7 +115,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         if (w > 0) {
             const bool mine = 2 * t0 + lane < rows;
             unsigned long long raw = raw_next;
-            while (!__all_sync(RSD_FULL, raw != RSD_LONG_SENTINEL)) {       // warp-uniform exit (see k_long_fwd)
+            while (!__all_sync(RSD_FULL, !mine || (unsigned)(raw >> 32) == gen)) {       // warp-uniform exit (see k_long_fwd)
                 if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
             }
             bval = (uint32_t)raw;

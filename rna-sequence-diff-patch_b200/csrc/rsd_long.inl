@@ -35,14 +35,17 @@ struct LongPairPlan {
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// carve the pair's buffers out of [base, ...); returns the bytes used (base == nullptr: size only)
+// boundary columns live in a buffer of their own (rsd_ctx::long_bound): it only ever holds tagged boundary words, so a
+// stale word can never pass for a published one (see LongJob2::gen)
+inline size_t long_bound_bytes(const LongPairPlan &P) { return al256((size_t)P.n_panels * (size_t)P.hb * 8); }
+
+// carve the pair's other buffers out of [base, ...); returns the bytes used (base == nullptr: size only)
 size_t long_layout(LongPairPlan &P, unsigned char *base, bool want_script, bool want_ij) {
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char *p = base ? base + off : nullptr; off += al256(bytes); return p; };
     P.da = (uint8_t *)take((size_t)P.m + 64); P.db = (uint8_t *)take((size_t)P.n + 64);
     unsigned char *small = take(256);
     P.keyacc = (long long *)small; P.dist = (double *)(small + 16); P.state = (int *)(small + 32); P.n_ops = (int32_t *)(small + 48);
-    P.bound = (unsigned long long *)take((size_t)P.n_panels * (size_t)P.hb * 8);
     if (want_script) {
         P.dirs = (uint32_t *)take((size_t)long2_dir_groups(P.hb) * (size_t)P.n_pad * 4 + 64);
         P.tmp = (uint8_t *)take((size_t)(P.m + P.n) + 64); P.op = (uint8_t *)take((size_t)(P.m + P.n) + 64);
@@ -156,17 +159,17 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         // memory budget: what is free now plus what this context already holds for long pairs
         size_t free_b = 0, total_b = 0;
         RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + c->long_pool.cap) * 0.85);
+        size_t budget = (size_t)((double)(free_b + c->long_pool.cap + c->long_bound.cap) * 0.85);
         if (const char *e = getenv("RSD_LONG_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
         // ---- per pair: one block if it fits, else row blocks x panel ranges ----
         for (int p = 0; p < n_pairs; ++p) if (P[p].eligible) {
             LongPairPlan &Q = P[p];
             Q.hb = Q.m; Q.nb = 1; Q.nr = (int)((Q.n_panels + max_ctas - 1) / max_ctas);
-            Q.need = long_layout(Q, nullptr, want_script != 0, want_ij);
+            Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q);
             if (Q.need > budget) {
                 LongPairPlan T = Q;
                 T.hb = 32; T.nb = 2;
-                const size_t fixed = long_layout(T, nullptr, want_script != 0, want_ij);       // everything but the per-row parts, at 32 rows
+                const size_t fixed = long_layout(T, nullptr, want_script != 0, want_ij) + long_bound_bytes(T);       // everything but the per-row parts, at 32 rows
                 const size_t per_row = (size_t)Q.n_panels * 8 + (want_script ? (size_t)Q.n_pad / 4 : 0);
                 // checkpoint rows: one per block boundary (4 bytes per column)
                 int64_t hb = 0;
@@ -187,7 +190,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     hb = h2;
                 }
                 Q.hb = hb; Q.nb = (int)((Q.m + hb - 1) / hb);
-                Q.need = long_layout(Q, nullptr, want_script != 0, want_ij);
+                Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q);
             }
         }
         // ---- batches: consecutive eligible pairs that fit the budget together; a blocked pair runs alone ----
@@ -205,10 +208,22 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             else while (at < order.size() && P[order[at]].nb == 1 && P[order[at]].nr == 1 && (batch.empty() || need + P[order[at]].need <= budget)) {
                 need += P[order[at]].need; batch.push_back(order[at]); ++at;
             }
-            RSD_OK_OR_RETURN(c->long_pool.ensure(need + 4096));
-            unsigned char *base = (unsigned char *)c->long_pool.p;
-            size_t off = 0;
-            for (int p : batch) { off += long_layout(P[p], base + off, want_script != 0, want_ij); }
+            size_t bound_need = 0;
+            for (int p : batch) bound_need += long_bound_bytes(P[p]);
+            RSD_OK_OR_RETURN(c->long_pool.ensure(need - bound_need + 4096));
+            {
+                // boundary words are tagged with a generation number instead of being reset before every launch: the
+                // buffer is zeroed when it is (re)allocated (tag 0 is never used), afterwards stale words carry older tags
+                const void *before = c->long_bound.p; const size_t before_cap = c->long_bound.cap;
+                RSD_OK_OR_RETURN(c->long_bound.ensure(bound_need + 256));
+                if (c->long_bound.p != before || c->long_bound.cap != before_cap) RSD_CUDA(cudaMemsetAsync(c->long_bound.p, 0, c->long_bound.cap, st));
+            }
+            unsigned char *base = (unsigned char *)c->long_pool.p, *bbase = (unsigned char *)c->long_bound.p;
+            size_t off = 0, boff = 0;
+            for (int p : batch) {
+                off += long_layout(P[p], base + off, want_script != 0, want_ij);
+                P[p].bound = (unsigned long long *)(bbase + boff); boff += long_bound_bytes(P[p]);
+            }
             for (int p : batch) {
                 LongPairPlan &Q = P[p];
                 RSD_CUDA(cudaMemcpyAsync(Q.da, a[p], (size_t)Q.m, cudaMemcpyHostToDevice, st));
@@ -218,10 +233,12 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             }
             // ---- job list of every launch of this batch ----
             std::vector<LongJob2> jobs;
-            struct Launch { int job0, n_jobs; bool dirs; int ring_job0[RSD_LONG2_MAX_RINGS + 1], ring_cta0[RSD_LONG2_MAX_RINGS + 1], n_rings; int memset_pair; int64_t memset_rows; int tb_pair, tb_r0; };
+            struct Launch { int job0, n_jobs; bool dirs; int ring_job0[RSD_LONG2_MAX_RINGS + 1], ring_cta0[RSD_LONG2_MAX_RINGS + 1], n_rings; int tb_pair, tb_r0; };
             std::vector<Launch> launches;
-            auto make_job = [&](const LongPairPlan &Q, int64_t r0, int64_t r1, int w_lo, int w_cnt, const uint32_t *top, uint32_t *bottom, bool dirs, bool recompute) {
+            auto next_gen = [&]() -> unsigned { if (++c->long_gen == 0u) c->long_gen = 1u; return c->long_gen; };       // (a wrap after 2^32 launch groups could meet a stale tag: ignored)
+            auto make_job = [&](const LongPairPlan &Q, int64_t r0, int64_t r1, int w_lo, int w_cnt, const uint32_t *top, uint32_t *bottom, bool dirs, bool recompute, unsigned gen) {
                 LongJob2 J{};
+                J.gen = gen;
                 J.a = Q.da; J.b = Q.db; J.m = (int)Q.m; J.n = (int)Q.n; J.r0 = (int)r0; J.r1 = (int)r1;
                 J.n_panels = Q.n_panels; J.n_pad = (int)Q.n_pad; J.w_lo = w_lo; J.w_cnt = w_cnt;
                 J.top = top; J.bottom = bottom; J.dirs = dirs ? Q.dirs : nullptr; J.bound = Q.bound; J.bstride = (int)Q.hb;
@@ -243,12 +260,13 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     for (int g = 0; g < G; ++g) { int width = 0; for (int p : ring[(size_t)g]) width = std::max(width, P[p].n_panels); cta += width; }
                     if (cta <= max_ctas || G == 1) break;
                 }
-                Launch L{}; L.job0 = 0; L.dirs = want_script != 0; L.n_rings = G; L.memset_pair = -1; L.tb_pair = -1;
+                Launch L{}; L.job0 = 0; L.dirs = want_script != 0; L.n_rings = G; L.tb_pair = -1;
+                const unsigned gen = next_gen();
                 int cta = 0;
                 for (int g = 0; g < G; ++g) {
                     L.ring_job0[g] = (int)jobs.size(); L.ring_cta0[g] = cta;
                     int width = 0;
-                    for (int p : ring[(size_t)g]) { jobs.push_back(make_job(P[p], 0, P[p].m, 0, P[p].n_panels, nullptr, nullptr, want_script != 0, false)); width = std::max(width, P[p].n_panels); }
+                    for (int p : ring[(size_t)g]) { jobs.push_back(make_job(P[p], 0, P[p].m, 0, P[p].n_panels, nullptr, nullptr, want_script != 0, false, gen)); width = std::max(width, P[p].n_panels); }
                     cta += width;
                 }
                 L.ring_job0[G] = (int)jobs.size(); L.ring_cta0[G] = cta; L.n_jobs = (int)jobs.size();
@@ -262,13 +280,13 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                 };
                 auto add_block = [&](int blk, bool dirs, bool recompute) {
                     const int64_t r0 = (int64_t)blk * Q.hb, r1 = std::min<int64_t>(Q.m, r0 + Q.hb);
+                    const unsigned gen = next_gen();                 // one tag per row block: its panel ranges read each other's columns
                     for (int r = 0; r < Q.nr; ++r) {
                         const int w_lo = (int)((int64_t)r * max_ctas), w_cnt = (int)std::min<int64_t>(max_ctas, Q.n_panels - w_lo);
                         Launch L{}; L.job0 = (int)jobs.size(); L.n_jobs = 1; L.dirs = dirs; L.n_rings = 1;
                         L.ring_job0[0] = 0; L.ring_job0[1] = 1; L.ring_cta0[0] = 0; L.ring_cta0[1] = w_cnt;
-                        L.memset_pair = r == 0 ? batch[0] : -1; L.memset_rows = r1 - r0;
                         L.tb_pair = (dirs && r == Q.nr - 1) ? batch[0] : -1; L.tb_r0 = (int)r0;
-                        jobs.push_back(make_job(Q, r0, r1, w_lo, w_cnt, ckpt_row(blk), recompute ? nullptr : ckpt_row(blk + 1), dirs, recompute));
+                        jobs.push_back(make_job(Q, r0, r1, w_lo, w_cnt, ckpt_row(blk), recompute ? nullptr : ckpt_row(blk + 1), dirs, recompute, gen));
                         launches.push_back(L);
                     }
                 };
@@ -293,15 +311,9 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             RSD_CUDA(cudaMemcpyAsync(jd, jobs.data(), jobs.size() * sizeof(LongJob2), cudaMemcpyHostToDevice, st));
             if (!tbs.empty()) RSD_CUDA(cudaMemcpyAsync(jd + jb, tbs.data(), tbs.size() * sizeof(LongTb2), cudaMemcpyHostToDevice, st));
             if (!ems.empty()) RSD_CUDA(cudaMemcpyAsync(jd + jb + tb, ems.data(), ems.size() * sizeof(LongEmit2), cudaMemcpyHostToDevice, st));
-            if (!solo) for (int p : batch)
-                RSD_CUDA(cudaMemsetAsync(P[p].bound, 0x80, (size_t)P[p].n_panels * (size_t)P[p].hb * 8, st));      // sentinel = "not published yet"
             if (c->timing && first_batch) RSD_CUDA(cudaEventRecord(c->ev0, st));
             int tb_at = 0;
             for (const Launch &L : launches) {
-                if (L.memset_pair >= 0) {
-                    const LongPairPlan &Q = P[L.memset_pair];
-                    RSD_CUDA(cudaMemsetAsync(Q.bound, 0x80, (size_t)Q.n_panels * (size_t)Q.hb * 8, st));
-                }
                 LongLaunch2 LL{};
                 LL.jobs = (const LongJob2 *)jd + L.job0; LL.n_rings = L.n_rings;
                 for (int g = 0; g <= L.n_rings; ++g) { LL.ring_job0[g] = L.ring_job0[g]; LL.ring_cta0[g] = L.ring_cta0[g]; }
@@ -349,7 +361,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     }
     // a pool of tens of GB (one huge pair) is not kept: the next call of any kind finds the memory free again; the pool
     // of an ordinary batch stays (cudaMalloc of 13 GB costs more than the batch itself)
-    if (c->long_pool.cap > ((size_t)32 << 30)) { RSD_CUDA(cudaStreamSynchronize(st)); c->long_pool.release(); }
+    if (c->long_pool.cap + c->long_bound.cap > ((size_t)32 << 30)) { RSD_CUDA(cudaStreamSynchronize(st)); c->long_pool.release(); c->long_bound.release(); }
     // ---- pairs that need the exact-double / fp64 kernels ----
     for (int p : fallback) {
         int mo = 0;

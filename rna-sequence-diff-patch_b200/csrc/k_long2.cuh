@@ -85,7 +85,11 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
     const unsigned long long *bin = w > 0 ? J.bound + (size_t)(w - 1) * J.bstride : nullptr;
     unsigned long long *bout = J.bound + (size_t)w * J.bstride;
     const bool publish = (w + 1 < J.n_panels);
-    const unsigned gen = J.gen;
+    // the tag is read from shared memory where it is needed (once per block): held in a register across the row loop it
+    // changed the allocator's schedule enough to cost a lone warp 4-9 % (one 50 kb pair: 5.7 instead of 5.5 ms)
+    volatile unsigned *s_gen = reinterpret_cast<volatile unsigned *>(s_pub + 32);
+    if (lane == 0) *s_gen = J.gen;
+    __syncwarp();
     uint32_t *dcol = DIRS ? J.dirs + col0 : nullptr;
     const int steps = (rows + 1) / 2 + 31 + 16;       // + one block so the last rows get published
     auto fetch = [&](int t0, int q) -> uint8_t { const int r = 2 * (t0 - 31) + lane + 32 * q; return ((unsigned)r < (unsigned)rows) ? __ldg(arow + r) : (uint8_t)0; };
@@ -105,7 +109,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         const uint32_t last_at_block_start = last1;
         if (publish) {
             const int r = 2 * (t0 - 47) + lane;
-            if (r >= 0 && r < rows) st_cg_u64(bout + r, ((unsigned long long)gen << 32) | (unsigned long long)s_pub[lane]);
+            if (r >= 0 && r < rows) st_cg_u64(bout + r, ((unsigned long long)*s_gen << 32) | (unsigned long long)s_pub[lane]);
         }
         __syncwarp();
         // The 32 boundary rows of this block were requested one block ahead (raw_next): once the panel runs far enough
@@ -115,6 +119,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         if (w > 0) {
             const bool mine = 2 * t0 + lane < rows;
             unsigned long long raw = raw_next;
+            const unsigned gen = *s_gen;
             while (!__all_sync(RSD_FULL, !mine || (unsigned)(raw >> 32) == gen)) {       // warp-uniform exit (see k_long_fwd)
                 if (mine) raw = ld_poll_u64(bin + 2 * t0 + lane);
             }
@@ -290,7 +295,7 @@ template <int C, bool DIRS, bool REL>
 __global__ void __launch_bounds__(32)
 k_long2(const LongLaunch2 L, const IntCosts *__restrict__ icp) {
     __shared__ uint32_t s_w[320];
-    __shared__ uint32_t s_pub[32];
+    __shared__ uint32_t s_pub[33];                  // [32]: the generation tag of the job in hand
     __shared__ __align__(4) uint8_t s_a[96];
     const int lane = threadIdx.x;
     int g = 0;

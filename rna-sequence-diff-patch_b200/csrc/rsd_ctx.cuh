@@ -103,8 +103,10 @@ struct rsd_ctx {
     int64_t dirs_budget_words = 0, dirs_budget_out_bytes = 0;     // chunk budget of the script path, measured once
     DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, s_tmp, p_out, p_len, p_err, misc;
     // long pairs (rsd_long.inl): one pool carved per batch, job tables
-    DevBuf long_pool, long_bound, long_jobs;
+    DevBuf long_pool, long_jobs;
+    size_t long_bound_hw = 0;              // head of long_pool that has only ever held tagged boundary words
     float long_fwd_ms = 0.f;
+    size_t long_budget = 0;                // memory budget of the long-pair planner (measured once, see rsd_long.inl)
     unsigned long_gen = 0;                 // generation tag of the boundary words (k_long2.cuh)
     // database shard
     SeqBufs db;
@@ -143,7 +145,7 @@ struct rsd_ctx {
         bufA.release(); bufB.release(); bufX.release(); bufQ.release(); db.release();
         for (PlanSlot &s : slots) s.release();
         DevBuf *all[] = {&out_f64, &mat_vals, &mat_mask, &mat_ab,
-                         &long_pool, &long_bound, &long_jobs, &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
+                         &long_pool, &long_jobs, &dirs, &s_op, &s_oi, &s_oj, &s_nops, &s_ok, &s_tmp, &p_out, &p_len, &p_err, &misc,
                          &db_dist, &db_topi, &db_tops, &db_aux, &db_perm, &sim_q, &sim_scores, &sim_aux, &sim_codes, &sim_work};
         for (DevBuf *b : all) b->release();
         d_stage.release(); for (int s = 0; s < 2; ++s) { raw_codes[s].release(); sym_start[s].release(); }

@@ -35,8 +35,8 @@ struct LongPairPlan {
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// boundary columns live in a buffer of their own (rsd_ctx::long_bound): it only ever holds tagged boundary words, so a
-// stale word can never pass for a published one (see LongJob2::gen)
+// boundary columns live at the head of the pool, a region that only ever holds tagged boundary words, so a stale word can
+// never pass for a published one (see LongJob2::gen and rsd_ctx::long_bound_hw)
 inline size_t long_bound_bytes(const LongPairPlan &P) { return al256((size_t)P.n_panels * (size_t)P.hb * 8); }
 
 // carve the pair's other buffers out of [base, ...); returns the bytes used (base == nullptr: size only)
@@ -81,8 +81,18 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         if (want_script && (!op[p] || max_ops[p] < Q.m + Q.n)) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: pair %d: script buffer missing or max_ops < m+n", p);
         if (Q.m == 0 || Q.n == 0) { Q.trivial = true; continue; }
         uint32_t sm = 0;
-        for (int64_t i = 0; i < Q.m; ++i) { if (a[p][i] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15"); sm |= 1u << a[p][i]; }
-        for (int64_t j = 0; j < Q.n; ++j) { if (b[p][j] > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15"); sm |= 1u << b[p][j]; }
+        for (int side = 0; side < 2; ++side) {                         // four independent accumulators: ~0.4 ns per symbol
+            const uint8_t *x = side ? b[p] : a[p]; const int64_t len = side ? Q.n : Q.m;
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0; unsigned hi = 0;
+            int64_t i = 0;
+            for (; i + 4 <= len; i += 4) {
+                hi |= x[i] | x[i + 1] | x[i + 2] | x[i + 3];
+                m0 |= 1u << (x[i] & 31); m1 |= 1u << (x[i + 1] & 31); m2 |= 1u << (x[i + 2] & 31); m3 |= 1u << (x[i + 3] & 31);
+            }
+            for (; i < len; ++i) { hi |= x[i]; m0 |= 1u << (x[i] & 31); }
+            if (hi > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15");
+            sm |= m0 | m1 | m2 | m3;
+        }
         symmask |= sm; max_m = std::max(max_m, Q.m); max_n = std::max(max_n, Q.n);
     }
     // Rings and panel width, from measurements on 50 kb pairs (tools/dbg_long_batch.py, profiles/r02_long_batch_sweep.log):
@@ -157,9 +167,13 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         int64_t max_ctas = (int64_t)per_sm * c->sm_count;
         if (const char *e = getenv("RSD_LONG_MAXCTAS")) max_ctas = std::max<int64_t>(1, std::min<int64_t>(max_ctas, atoll(e)));
         // memory budget: what is free now plus what this context already holds for long pairs
-        size_t free_b = 0, total_b = 0;
-        RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + c->long_pool.cap + c->long_bound.cap) * 0.85);
+        // (cudaMemGetInfo costs ~15 ms per call on this driver: asked once per context, and again after a failed allocation)
+        if (c->long_budget == 0) {
+            size_t free_b = 0, total_b = 0;
+            RSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            c->long_budget = (size_t)((double)(free_b + c->long_pool.cap) * 0.85);
+        }
+        size_t budget = c->long_budget;
         if (const char *e = getenv("RSD_LONG_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
         // ---- per pair: one block if it fits, else row blocks x panel ranges ----
         for (int p = 0; p < n_pairs; ++p) if (P[p].eligible) {
@@ -210,15 +224,20 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             }
             size_t bound_need = 0;
             for (int p : batch) bound_need += long_bound_bytes(P[p]);
-            RSD_OK_OR_RETURN(c->long_pool.ensure(need - bound_need + 4096));
+            // Boundary words are tagged with a generation number instead of being reset before every launch.  That is only
+            // safe where nothing but boundary words has ever been stored: they occupy the head of the pool, [0, long_bound_hw),
+            // a region that only grows; the part it grows into is zeroed once (tag 0 is never used), and a new pool starts over.
             {
-                // boundary words are tagged with a generation number instead of being reset before every launch: the
-                // buffer is zeroed when it is (re)allocated (tag 0 is never used), afterwards stale words carry older tags
-                const void *before = c->long_bound.p; const size_t before_cap = c->long_bound.cap;
-                RSD_OK_OR_RETURN(c->long_bound.ensure(bound_need + 256));
-                if (c->long_bound.p != before || c->long_bound.cap != before_cap) RSD_CUDA(cudaMemsetAsync(c->long_bound.p, 0, c->long_bound.cap, st));
+                const void *before = c->long_pool.p; const size_t before_cap = c->long_pool.cap;
+                const size_t head = std::max(c->long_bound_hw, bound_need);
+                if (int rc = c->long_pool.ensure(head + (need - bound_need) + 4096)) { c->long_budget = 0; c->long_bound_hw = 0; return rc; }   // other allocations moved in: measure again next time
+                if (c->long_pool.p != before || c->long_pool.cap != before_cap) c->long_bound_hw = 0;
+                if (bound_need > c->long_bound_hw) {
+                    RSD_CUDA(cudaMemsetAsync((unsigned char *)c->long_pool.p + c->long_bound_hw, 0, bound_need - c->long_bound_hw, st));
+                    c->long_bound_hw = bound_need;
+                }
             }
-            unsigned char *base = (unsigned char *)c->long_pool.p, *bbase = (unsigned char *)c->long_bound.p;
+            unsigned char *bbase = (unsigned char *)c->long_pool.p, *base = bbase + c->long_bound_hw;
             size_t off = 0, boff = 0;
             for (int p : batch) {
                 off += long_layout(P[p], base + off, want_script != 0, want_ij);
@@ -361,7 +380,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     }
     // a pool of tens of GB (one huge pair) is not kept: the next call of any kind finds the memory free again; the pool
     // of an ordinary batch stays (cudaMalloc of 13 GB costs more than the batch itself)
-    if (c->long_pool.cap + c->long_bound.cap > ((size_t)32 << 30)) { RSD_CUDA(cudaStreamSynchronize(st)); c->long_pool.release(); c->long_bound.release(); }
+    if (c->long_pool.cap > ((size_t)32 << 30)) { RSD_CUDA(cudaStreamSynchronize(st)); c->long_pool.release(); c->long_bound_hw = 0; }
     // ---- pairs that need the exact-double / fp64 kernels ----
     for (int p : fallback) {
         int mo = 0;

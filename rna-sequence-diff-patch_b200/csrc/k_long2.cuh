@@ -36,6 +36,10 @@ struct LongJob2 {
 __host__ __device__ inline long long long2_dir_groups(long long rows) { return rows / 16 + 8; }
 
 #define RSD_LONG2_MAX_RINGS 16
+#ifndef RSD_LONG2_UNROLL
+#define RSD_LONG2_UNROLL 2             // steps of the row loop unrolled together (build-time knob)
+#endif
+constexpr int LONG2_UNROLL = RSD_LONG2_UNROLL;
 struct LongLaunch2 {
     const LongJob2 *jobs;                          // device array, ring after ring
     int n_rings;
@@ -143,7 +147,7 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         constexpr bool STEADY = decltype(steady_tag)::value;
 #pragma unroll 1
         for (int k8 = 0; k8 < 16; k8 += 8) {
-#pragma unroll 2
+#pragma unroll (LONG2_UNROLL)
         for (int kk = 0; kk < 8; ++kk) {
             const int k = k8 + kk;
             const int i0 = 2 * (t0 + k - lane);

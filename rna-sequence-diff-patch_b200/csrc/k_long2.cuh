@@ -35,7 +35,7 @@ struct LongJob2 {
 // rows of direction-word groups a row block of `rows` rows needs (skew of the last lane + the publication tail)
 __host__ __device__ inline long long long2_dir_groups(long long rows) { return rows / 16 + 8; }
 
-#define RSD_LONG2_MAX_RINGS 16
+#define RSD_LONG2_MAX_RINGS 128
 #ifndef RSD_LONG2_UNROLL
 #define RSD_LONG2_UNROLL 2             // steps of the row loop unrolled together (build-time knob)
 #endif
@@ -317,7 +317,7 @@ struct LongTb2 {
     int m, n, r0, n_pad, C;        // C: columns per lane of the forward kernel (the skew of a column's words is 2 * its lane)
     const uint32_t *dirs;          // direction words of the rows r0 .. (block-relative and skewed, as the forward kernel wrote them)
     uint8_t *tmp;                  // [m + n]
-    int *state;                    // {i, j, pos}; i < 0 = not started (start at (m, n))
+    int *state;                    // {i, j, pos, started}; started == 0: begin at (m, n)
     int32_t *n_ops;
     int last;                      // this is the pair's top block (r0 == 0): finish the borders and count
 };
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restric
     const LongTb2 J = jobs[blockIdx.x];
     const int lane = threadIdx.x;
     int i = J.state[0], j = J.state[1], pos = J.state[2];
-    if (i < 0) { i = J.m; j = J.n; pos = J.m + J.n; }
+    if (J.state[3] == 0) { i = J.m; j = J.n; pos = J.m + J.n; }
     const int r0 = J.r0, n_pad = J.n_pad;
     const int logC = J.C == 4 ? 2 : J.C == 8 ? 3 : 4;
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(32) k_long2_traceback(const LongTb2 *__restric
         pos -= ni; i = 0; j = 0;
         if (lane == 0) J.n_ops[0] = J.m + J.n - pos;
     }
-    if (lane == 0) { J.state[0] = i; J.state[1] = j; J.state[2] = pos; }
+    if (lane == 0) { J.state[0] = i; J.state[1] = j; J.state[2] = pos; J.state[3] = 1; }
 }
 
 // packed scripts of a batch: k_long_emit per pair

@@ -1203,6 +1203,48 @@ static int script_common(rsd_ctx *c, const uint32_t *a_words, const int64_t *a_s
     if (max_ops < 1) return rsd_fail(RSD_EINVAL, "rsd_script: max_ops must be >= 1");
     RSD_OK_OR_RETURN(c->ensure_device());
     if (n_pairs == 0) { if (mode_out) *mode_out = 0; return RSD_OK; }
+    // A batch whose cells lie mostly in pairs of several thousand symbols goes to the panel-wavefront kernels
+    // (rsd_long_pairs): one warp per pair with tape passes, the design of k_script_fwd for 1-2 kb pairs, falls to
+    // 450 / 240 / 35 GCUPS at 5 / 10 / 20 kb, where the panel pipeline runs at 1.0-1.4 TCUPS with the same scripts
+    // (tools/dbg_mid_pairs.py).  Not for the round-trip-checking variant (ok != NULL), which patches on the device.
+    if (!ok && n_pairs <= 65536 && !getenv("RSD_SCRIPT_NO_LONG")) {
+        int64_t T = 4096;
+        if (const char *e = getenv("RSD_SCRIPT_LONG_MIN")) T = std::max<int64_t>(atoll(e), 1);
+        double cells_all = 0, cells_long = 0; int64_t total = 0;
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            if (a_len[p] < 0 || b_len[p] < 0) return rsd_fail(RSD_EINVAL, "rsd_script: negative length");
+            const double cells = (double)a_len[p] * (double)b_len[p];
+            cells_all += cells; total += (int64_t)a_len[p] + b_len[p];
+            if (std::max(a_len[p], b_len[p]) >= T) cells_long += cells;
+        }
+        if (cells_long > 0.5 * cells_all) {
+            const int per = 32 / bits; const uint32_t msk = (1u << bits) - 1u;
+            std::vector<uint8_t> codes((size_t)total + 16);
+            std::vector<const uint8_t *> pa((size_t)n_pairs), pb((size_t)n_pairs);
+            std::vector<int64_t> lm((size_t)n_pairs), ln((size_t)n_pairs), mo((size_t)n_pairs), no64((size_t)n_pairs, 0);
+            std::vector<uint8_t *> pop((size_t)n_pairs); std::vector<int32_t *> poi((size_t)n_pairs), poj((size_t)n_pairs);
+            std::vector<int> modes((size_t)n_pairs, 0);
+            size_t at = 0;
+            for (int64_t p = 0; p < n_pairs; ++p) {
+                for (int side = 0; side < 2; ++side) {
+                    const uint32_t *w = side ? b_words : a_words; const int64_t st0 = side ? b_start[p] : a_start[p];
+                    const int32_t len = side ? b_len[p] : a_len[p]; const int64_t nw = side ? b_nwords : a_nwords;
+                    if (st0 < 0 || st0 + ((int64_t)len + per - 1) / per > nw) return rsd_fail(RSD_EINVAL, "rsd_script: pair %lld lies outside the word buffer", (long long)p);
+                    (side ? pb : pa)[(size_t)p] = codes.data() + at;
+                    for (int32_t j = 0; j < len; ++j) codes[at++] = (uint8_t)((w[st0 + j / per] >> ((j % per) * bits)) & msk);
+                }
+                lm[(size_t)p] = a_len[p]; ln[(size_t)p] = b_len[p]; mo[(size_t)p] = max_ops;
+                if ((int64_t)a_len[p] + b_len[p] > max_ops) return rsd_fail(RSD_EINVAL, "rsd_script: max_ops too small for pair %lld", (long long)p);
+                pop[(size_t)p] = op + (size_t)p * max_ops;
+                poi[(size_t)p] = oi ? oi + (size_t)p * max_ops : nullptr; poj[(size_t)p] = oj ? oj + (size_t)p * max_ops : nullptr;
+            }
+            RSD_OK_OR_RETURN(rsd_long_pairs(c, (int)n_pairs, pa.data(), lm.data(), pb.data(), ln.data(), force_mode == RSD_MODE_I16X2 ? 0 : force_mode, 1, mo.data(),
+                                            pop.data(), poi.data(), poj.data(), no64.data(), dist, modes.data()));
+            for (int64_t p = 0; p < n_pairs; ++p) n_ops[p] = (int32_t)no64[(size_t)p];
+            if (mode_out) { int mm = 0; for (int x : modes) mm = std::max(mm, x); *mode_out = mm; }
+            return RSD_OK;
+        }
+    }
     RSD_OK_OR_RETURN(c->upload_seqs(c->bufA, a_words, a_start, a_len, n_pairs, a_nwords, c->stream));
     RSD_OK_OR_RETURN(c->upload_seqs(c->bufB, b_words, b_start, b_len, n_pairs, b_nwords, c->stream));
     return c->script_pipeline(a_len, b_len, n_pairs, bits, symmask, force_mode, max_ops, false, op, oi, oj, n_ops, dist, ok, mode_out);

@@ -104,6 +104,7 @@ struct rsd_ctx {
     DevBuf dirs, s_op, s_oi, s_oj, s_nops, s_ok, s_tmp, p_out, p_len, p_err, misc;
     // long pairs (rsd_long.inl): one pool carved per batch, job tables
     DevBuf long_pool, long_jobs;
+    void *long_hstage = nullptr; size_t long_hstage_cap = 0;     // pinned staging of rsd_long_pairs
     size_t long_bound_hw = 0;              // head of long_pool that has only ever held tagged boundary words
     float long_fwd_ms = 0.f;
     size_t long_budget = 0;                // memory budget of the long-pair planner (measured once, see rsd_long.inl)
@@ -150,5 +151,6 @@ struct rsd_ctx {
         for (DevBuf *b : all) b->release();
         d_stage.release(); for (int s = 0; s < 2; ++s) { raw_codes[s].release(); sym_start[s].release(); }
         if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; h_stage_cap = 0; }
+        if (long_hstage) { cudaFreeHost(long_hstage); long_hstage = nullptr; long_hstage_cap = 0; }
     }
 };

@@ -41,18 +41,23 @@ inline size_t long_bound_bytes(const LongPairPlan &P) { return al256((size_t)P.n
 
 // carve the pair's other buffers out of [base, ...); returns the bytes used (base == nullptr: size only)
 size_t long_layout(LongPairPlan &P, unsigned char *base, bool want_script, bool want_ij) {
+    (void)want_ij;
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char *p = base ? base + off : nullptr; off += al256(bytes); return p; };
-    P.da = (uint8_t *)take((size_t)P.m + 64); P.db = (uint8_t *)take((size_t)P.n + 64);
-    unsigned char *small = take(256);
-    P.keyacc = (long long *)small; P.dist = (double *)(small + 16); P.state = (int *)(small + 32); P.n_ops = (int32_t *)(small + 48);
     if (want_script) {
         P.dirs = (uint32_t *)take((size_t)long2_dir_groups(P.hb) * (size_t)P.n_pad * 4 + 64);
-        P.tmp = (uint8_t *)take((size_t)(P.m + P.n) + 64); P.op = (uint8_t *)take((size_t)(P.m + P.n) + 64);
-        if (want_ij) { P.oi = (int32_t *)take(4 * (size_t)(P.m + P.n) + 64); P.oj = (int32_t *)take(4 * (size_t)(P.m + P.n) + 64); }
+        P.tmp = (uint8_t *)take((size_t)(P.m + P.n) + 64);
     }
     if (P.nb > 1) P.ckpt = (uint32_t *)take((size_t)(want_script ? P.nb - 1 : 2) * (size_t)P.n_pad * 4);
     return off;
+}
+// The pairs of a batch share four contiguous regions so that inputs and results cross PCIe in a handful of copies through
+// a pinned staging buffer instead of five small pageable copies per pair: sequences (a then b of every pair), 64 bytes
+// of scalars per pair (exact key accumulators, distance, traceback state, op count), and the packed scripts (op, oi, oj).
+inline size_t long_seq_bytes(const LongPairPlan &P) { return al256((size_t)P.m + 64) + al256((size_t)P.n + 64); }
+inline size_t long_ops_slot(const LongPairPlan &P) { return al256((size_t)(P.m + P.n) + 64); }                 // entries, not bytes
+inline size_t long_shared_bytes(const LongPairPlan &P, bool want_script, bool want_ij) {
+    return long_seq_bytes(P) + 64 + (want_script ? long_ops_slot(P) * (want_ij ? 9 : 1) : 0);
 }
 
 }  // namespace
@@ -102,13 +107,13 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     // the batch has pairs for at least two rounds of them, else one ring per pair (up to 16: a second round would cost
     // more than the contention); 16 columns per lane once ~700 warps are in flight at 8, else 8 (a lone warp's step
     // hardly grows from 4 to 8 columns, so 4 never wins).
-    int rings_want = 16;
+    int rings_want = 1;
     {
         int nk = 0; double sum_n = 0;
         for (int p = 0; p < n_pairs; ++p) if (!P[p].trivial) { ++nk; sum_n += (double)P[p].n; }
         const double avg_n = nk ? sum_n / nk : 0.0;
-        const int r_star = (int)std::min(16.0, std::max(1.0, std::floor(1200.0 / std::max(1.0, avg_n / 512.0) + 0.5)));
-        rings_want = nk <= std::min(16, r_star + 4) ? std::max(nk, 1) : r_star;
+        const int r_star = (int)std::min((double)RSD_LONG2_MAX_RINGS, std::max(1.0, std::floor(1200.0 / std::max(1.0, std::ceil(avg_n / 512.0)) + 0.5)));
+        rings_want = nk <= std::min(RSD_LONG2_MAX_RINGS, r_star + r_star / 3) ? std::max(nk, 1) : r_star;
         if (const char *e = getenv("RSD_LONG_RINGS")) rings_want = std::min(std::max(atoi(e), 1), RSD_LONG2_MAX_RINGS);
         C = (double)std::min(nk, rings_want) * (avg_n / 256.0) >= 700.0 ? 16 : 8;
         if (const char *e = getenv("RSD_LONG_C")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) C = v; }
@@ -179,11 +184,11 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
         for (int p = 0; p < n_pairs; ++p) if (P[p].eligible) {
             LongPairPlan &Q = P[p];
             Q.hb = Q.m; Q.nb = 1; Q.nr = (int)((Q.n_panels + max_ctas - 1) / max_ctas);
-            Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q);
+            Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q) + long_shared_bytes(Q, want_script != 0, want_ij);
             if (Q.need > budget) {
                 LongPairPlan T = Q;
                 T.hb = 32; T.nb = 2;
-                const size_t fixed = long_layout(T, nullptr, want_script != 0, want_ij) + long_bound_bytes(T);       // everything but the per-row parts, at 32 rows
+                const size_t fixed = long_layout(T, nullptr, want_script != 0, want_ij) + long_bound_bytes(T) + long_shared_bytes(T, want_script != 0, want_ij);       // everything but the per-row parts, at 32 rows
                 const size_t per_row = (size_t)Q.n_panels * 8 + (want_script ? (size_t)Q.n_pad / 4 : 0);
                 // checkpoint rows: one per block boundary (4 bytes per column)
                 int64_t hb = 0;
@@ -204,7 +209,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     hb = h2;
                 }
                 Q.hb = hb; Q.nb = (int)((Q.m + hb - 1) / hb);
-                Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q);
+                Q.need = long_layout(Q, nullptr, want_script != 0, want_ij) + long_bound_bytes(Q) + long_shared_bytes(Q, want_script != 0, want_ij);
             }
         }
         // ---- batches: consecutive eligible pairs that fit the budget together; a blocked pair runs alone ----
@@ -239,16 +244,44 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             }
             unsigned char *bbase = (unsigned char *)c->long_pool.p, *base = bbase + c->long_bound_hw;
             size_t off = 0, boff = 0;
+            // shared regions first: [sequences][scalars][op][oi][oj]
+            size_t seq_bytes = 0, ops_entries = 0;
+            for (int p : batch) { seq_bytes += long_seq_bytes(P[p]); ops_entries += long_ops_slot(P[p]); }
+            const size_t small_bytes = al256(64 * batch.size());
+            unsigned char *d_seq = base + off; off += seq_bytes;
+            unsigned char *d_small = base + off; off += small_bytes;
+            uint8_t *d_op = nullptr; int32_t *d_oi = nullptr, *d_oj = nullptr;
+            if (want_script) {
+                d_op = base + off; off += ops_entries;
+                if (want_ij) { d_oi = (int32_t *)(base + off); off += 4 * ops_entries; d_oj = (int32_t *)(base + off); off += 4 * ops_entries; }
+            }
+            // pinned staging: sequences on the way in, scalars and scripts on the way out
+            const size_t out_bytes = small_bytes + (want_script ? ops_entries * (want_ij ? 9 : 1) : 0);
+            const size_t stage_need = std::max(seq_bytes, out_bytes) + 256;
+            if (stage_need > c->long_hstage_cap) {
+                if (c->long_hstage) cudaFreeHost(c->long_hstage);
+                c->long_hstage = nullptr; c->long_hstage_cap = 0;
+                RSD_CUDA(cudaMallocHost(&c->long_hstage, stage_need + stage_need / 4));
+                c->long_hstage_cap = stage_need + stage_need / 4;
+            }
+            unsigned char *hst = (unsigned char *)c->long_hstage;
+            {
+                size_t so = 0, oo = 0, q = 0;
+                for (int p : batch) {
+                    LongPairPlan &Q = P[p];
+                    Q.da = d_seq + so; memcpy(hst + so, a[p], (size_t)Q.m); so += al256((size_t)Q.m + 64);
+                    Q.db = d_seq + so; memcpy(hst + so, b[p], (size_t)Q.n); so += al256((size_t)Q.n + 64);
+                    unsigned char *small = d_small + 64 * q;
+                    Q.keyacc = (long long *)small; Q.dist = (double *)(small + 16); Q.state = (int *)(small + 32); Q.n_ops = (int32_t *)(small + 48);
+                    if (want_script) { Q.op = d_op + oo; if (want_ij) { Q.oi = d_oi + oo; Q.oj = d_oj + oo; } oo += long_ops_slot(Q); }
+                    ++q;
+                }
+            }
+            RSD_CUDA(cudaMemcpyAsync(d_seq, hst, seq_bytes, cudaMemcpyHostToDevice, st));
+            RSD_CUDA(cudaMemsetAsync(d_small, 0, small_bytes, st));                 // key accumulators 0, traceback "not started"
             for (int p : batch) {
                 off += long_layout(P[p], base + off, want_script != 0, want_ij);
                 P[p].bound = (unsigned long long *)(bbase + boff); boff += long_bound_bytes(P[p]);
-            }
-            for (int p : batch) {
-                LongPairPlan &Q = P[p];
-                RSD_CUDA(cudaMemcpyAsync(Q.da, a[p], (size_t)Q.m, cudaMemcpyHostToDevice, st));
-                RSD_CUDA(cudaMemcpyAsync(Q.db, b[p], (size_t)Q.n, cudaMemcpyHostToDevice, st));
-                RSD_CUDA(cudaMemsetAsync(Q.keyacc, 0, 64, st));
-                RSD_CUDA(cudaMemsetAsync(Q.state, 0xff, 12, st));                 // i < 0: traceback not started
             }
             // ---- job list of every launch of this batch ----
             std::vector<LongJob2> jobs;
@@ -353,24 +386,34 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             }
             if (c->timing) { RSD_CUDA(cudaEventRecord(c->ev1, st)); c->timed = true; }
             RSD_CUDA(cudaGetLastError());
-            // ---- results ----
-            std::vector<int32_t> k32(batch.size(), 0);
-            for (size_t q = 0; q < batch.size(); ++q) {
-                const LongPairPlan &Q = P[batch[q]];
-                RSD_CUDA(cudaMemcpyAsync(&dist[batch[q]], Q.dist, sizeof(double), cudaMemcpyDeviceToHost, st));
-                if (want_script) RSD_CUDA(cudaMemcpyAsync(&k32[q], Q.n_ops, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            // ---- results: scalars and scripts in (at most) four copies into the staging buffer, then out to the caller ----
+            // (the host has to be done with the staged sequences before they are overwritten: the stream order guarantees it)
+            RSD_CUDA(cudaMemcpyAsync(hst, d_small, small_bytes, cudaMemcpyDeviceToHost, st));
+            unsigned char *h_op = hst + small_bytes, *h_oi = h_op + ops_entries, *h_oj = h_oi + 4 * ops_entries;
+            if (want_script) {
+                RSD_CUDA(cudaMemcpyAsync(h_op, d_op, ops_entries, cudaMemcpyDeviceToHost, st));
+                if (want_ij) {
+                    RSD_CUDA(cudaMemcpyAsync(h_oi, d_oi, 4 * ops_entries, cudaMemcpyDeviceToHost, st));
+                    RSD_CUDA(cudaMemcpyAsync(h_oj, d_oj, 4 * ops_entries, cudaMemcpyDeviceToHost, st));
+                }
             }
             RSD_CUDA(cudaStreamSynchronize(st));
             if (c->timing) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev_t1[0]) == cudaSuccess) fwd_ms_total = ms; }
-            if (want_script) {
+            {
+                size_t oo = 0;
                 for (size_t q = 0; q < batch.size(); ++q) {
                     const int p = batch[q]; const LongPairPlan &Q = P[p];
-                    n_ops[p] = k32[q];
-                    RSD_CUDA(cudaMemcpyAsync(op[p], Q.op, (size_t)k32[q], cudaMemcpyDeviceToHost, st));
-                    if (oi && oi[p]) RSD_CUDA(cudaMemcpyAsync(oi[p], Q.oi, sizeof(int32_t) * (size_t)k32[q], cudaMemcpyDeviceToHost, st));
-                    if (oj && oj[p]) RSD_CUDA(cudaMemcpyAsync(oj[p], Q.oj, sizeof(int32_t) * (size_t)k32[q], cudaMemcpyDeviceToHost, st));
+                    const unsigned char *small = hst + 64 * q;
+                    memcpy(&dist[p], small + 16, sizeof(double));
+                    if (want_script) {
+                        int32_t k32 = 0; memcpy(&k32, small + 48, sizeof k32);
+                        n_ops[p] = k32;
+                        memcpy(op[p], h_op + oo, (size_t)k32);
+                        if (oi && oi[p]) memcpy(oi[p], h_oi + 4 * oo, sizeof(int32_t) * (size_t)k32);
+                        if (oj && oj[p]) memcpy(oj[p], h_oj + 4 * oo, sizeof(int32_t) * (size_t)k32);
+                        oo += long_ops_slot(Q);
+                    }
                 }
-                RSD_CUDA(cudaStreamSynchronize(st));
             }
             if (ltrace) fprintf(stderr, "[rsd trace] long batch: %zu pair(s)%s, %zu launch(es), %zu MB, blocks %d x ranges %d of pair %d\n", batch.size(), solo ? " (blocked)" : "",
                                 launches.size(), need >> 20, P[batch[0]].nb, P[batch[0]].nr, batch[0]);

@@ -182,3 +182,31 @@ def test_edit_script_entry_point_any_length(R, eng, golden, monkeypatch):
     monkeypatch.setenv("RSD_LONG_BUDGET_MB", "6")
     assert sed.edit_script(a, b, costs, engine=eng) == want
     assert sed.patching(want, a) == (0, b)
+
+
+def test_script_batch_routes_long_pairs_to_the_panel_kernels(R, eng, golden, monkeypatch):
+    """A batch whose cells lie mostly in pairs of >= 4096 symbols runs on rsd_long_pairs (rings of panel pipelines)
+    instead of one warp per pair: same packed scripts, distances and counts as the unrouted path and as the oracle;
+    short pairs and an empty side in the same batch included."""
+    rng = np.random.default_rng(4242)
+    lens = [(5000, 5200), (4100, 300), (37, 4500), (6000, 6000), (800, 900), (0, 5), (4999, 4097)]
+    a = ["".join(rng.choice(list("AGCU"), size=m)) for m, _ in lens]
+    b = ["".join(rng.choice(list("AGCU"), size=n)) for _, n in lens]
+    b[3] = a[3][:2500] + "".join(rng.choice(list("AGCU"), size=1000)) + a[3][3500:]          # homologous: long tie runs
+    costs = golden["default_costs"]
+    eng.set_costs(costs)
+    A, B = R.pack(a), R.pack(b)
+    launches0 = eng.launch_count()
+    routed = eng.script_batch(A, B)
+    n_routed = eng.launch_count() - launches0
+    monkeypatch.setenv("RSD_SCRIPT_NO_LONG", "1")
+    plain = eng.script_batch(A, B)
+    assert n_routed <= 4                                  # one forward launch, traceback, emit
+    for p in range(len(lens)):
+        k = plain["n_ops"][p]
+        assert routed["n_ops"][p] == k and routed["dist"][p] == plain["dist"][p]
+        for key in ("op", "oi", "oj"):
+            assert np.array_equal(routed[key][p, :k], plain[key][p, :k]), (p, key)
+        if lens[p][0] and lens[p][1]:
+            ops, oi, oj, d = O.canonical_script(a[p], b[p], costs)
+            assert d == routed["dist"][p] and np.array_equal(routed["op"][p, :k], ops) and np.array_equal(routed["oj"][p, :k], oj)

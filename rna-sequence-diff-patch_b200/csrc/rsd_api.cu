@@ -891,6 +891,49 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     return RSD_OK;
 }
 
+// Batches whose cells lie mostly in pairs of several thousand symbols: the panel-wavefront kernels (rsd_long_pairs,
+// distance only) run them at 2.7 TCUPS where one warp per pair with tape passes manages 1.0 / 0.5 / 0.25 TCUPS at
+// 5 / 10 / 20 kb (tools/dbg_mid_pairs.py).  -> 1 routed (out filled), 0 not applicable, < 0 error.
+static int distance_route_long(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int bits, int force_mode, double *out, int *mode_out) {
+    if (n_pairs > 65536 || force_mode == RSD_MODE_I16X2 || getenv("RSD_DIST_NO_LONG")) return 0;      // (a forced int16x2 mode keeps its own applicability error)
+    int64_t T = 4096;
+    if (const char *e = getenv("RSD_DIST_LONG_MIN")) T = std::max<int64_t>(atoll(e), 1);
+    double cells_all = 0, cells_long = 0; int64_t total[2] = {0, 0};
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int32_t m = in[0].len[p], n = in[1].len[p];
+        if (m < 0 || n < 0) return -rsd_fail(RSD_EINVAL, "rsd_distance_batch: negative length");
+        const double cells = (double)m * (double)n;
+        cells_all += cells; total[0] += m; total[1] += n;
+        if (std::max(m, n) >= T) cells_long += cells;
+    }
+    if (!(cells_long > 0.5 * cells_all)) return 0;
+    const int per = 32 / bits; const uint32_t msk = (1u << bits) - 1u;
+    std::vector<uint8_t> codes[2];
+    std::vector<const uint8_t *> ptr[2]; std::vector<int64_t> len64[2];
+    for (int s = 0; s < 2; ++s) {
+        ptr[s].resize((size_t)n_pairs); len64[s].resize((size_t)n_pairs);
+        if (!in[s].codes) codes[s].resize((size_t)total[s] + 16);
+        int64_t at = 0, wat = 0;                      // symbol / word offset of the canonical layouts
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            const int32_t len = in[s].len[p];
+            len64[s][(size_t)p] = len;
+            if (in[s].codes) { ptr[s][(size_t)p] = in[s].codes + at; at += len; continue; }
+            const int64_t st0 = in[s].start ? in[s].start[p] : wat;
+            const int64_t nw = ((int64_t)len + per - 1) / per;
+            if (st0 < 0 || st0 + nw > in[s].nwords) return -rsd_fail(RSD_EINVAL, "rsd_distance_batch: pair %lld lies outside the word buffer", (long long)p);
+            ptr[s][(size_t)p] = codes[s].data() + at;
+            for (int32_t j = 0; j < len; ++j) codes[s][(size_t)at++] = (uint8_t)((in[s].words[st0 + j / per] >> ((j % per) * bits)) & msk);
+            wat += nw;
+        }
+    }
+    std::vector<int> modes((size_t)n_pairs, 0);
+    const int rc = rsd_long_pairs(c, (int)n_pairs, ptr[0].data(), len64[0].data(), ptr[1].data(), len64[1].data(), force_mode == RSD_MODE_I16X2 ? 0 : force_mode, 0,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, out, modes.data());
+    if (rc) return -rc;
+    if (mode_out) { int mm = 0; for (int x : modes) mm = std::max(mm, x); *mode_out = mm; }
+    return 1;
+}
+
 extern "C" int rsd_distance_batch(rsd_ctx *c,
                                   const uint32_t *a_words, const int64_t *a_start, const int32_t *a_len, int64_t a_nwords,
                                   const uint32_t *b_words, const int64_t *b_start, const int32_t *b_len, int64_t b_nwords,
@@ -904,6 +947,7 @@ extern "C" int rsd_distance_batch(rsd_ctx *c,
     RSD_OK_OR_RETURN(c->ensure_device());
     if (n_pairs == 0) return RSD_OK;
     const SideIn in[2] = {{a_words, a_start, a_len, a_nwords, nullptr}, {b_words, b_start, b_len, b_nwords, nullptr}};
+    if (const int r = distance_route_long(c, in, n_pairs, bits, force_mode, out, mode_out)) return r > 0 ? RSD_OK : -r;
     return distance_host(c, in, n_pairs, max_m_hint, max_n_hint, bits, symmask, force_mode, out, mode_out);
 }
 
@@ -922,6 +966,7 @@ extern "C" int rsd_distance_batch_codes(rsd_ctx *c, const uint8_t *a_codes, cons
     if (n_pairs == 0) return RSD_OK;
     // (negative lengths are caught by the block sums of distance_host: no extra pass over the 8 bytes per pair)
     const SideIn in[2] = {{nullptr, nullptr, a_len, 0, a_codes}, {nullptr, nullptr, b_len, 0, b_codes}};
+    if (const int r = distance_route_long(c, in, n_pairs, bits, force_mode, out, mode_out)) return r > 0 ? RSD_OK : -r;
     return distance_host(c, in, n_pairs, max_m_hint, max_n_hint, bits, symmask, force_mode, out, mode_out);
 }
 
@@ -1207,7 +1252,7 @@ static int script_common(rsd_ctx *c, const uint32_t *a_words, const int64_t *a_s
     // (rsd_long_pairs): one warp per pair with tape passes, the design of k_script_fwd for 1-2 kb pairs, falls to
     // 450 / 240 / 35 GCUPS at 5 / 10 / 20 kb, where the panel pipeline runs at 1.0-1.4 TCUPS with the same scripts
     // (tools/dbg_mid_pairs.py).  Not for the round-trip-checking variant (ok != NULL), which patches on the device.
-    if (!ok && n_pairs <= 65536 && !getenv("RSD_SCRIPT_NO_LONG")) {
+    if (!ok && n_pairs <= 65536 && force_mode != RSD_MODE_I16X2 && !getenv("RSD_SCRIPT_NO_LONG")) {
         int64_t T = 4096;
         if (const char *e = getenv("RSD_SCRIPT_LONG_MIN")) T = std::max<int64_t>(atoll(e), 1);
         double cells_all = 0, cells_long = 0; int64_t total = 0;

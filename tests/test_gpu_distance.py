@@ -358,3 +358,31 @@ def test_pair_list_shards_concatenate_to_the_unsharded_result(R, eng, golden):
         assert parts[-1].shape[0] == hi - lo
     assert np.array_equal(np.concatenate(parts), whole)
     assert np.array_equal(whole, oracle_batch(a, b, golden["default_costs"]))
+
+
+def test_distance_batch_routes_long_pairs_to_the_panel_kernels(R, eng, golden, monkeypatch):
+    """Batches whose cells lie mostly in pairs of >= 4096 symbols run on rsd_long_pairs (distance only): same numbers as
+    the tape-pass kernels and the oracle, from packed words (explicit and canonical layout) and from raw codes."""
+    import ctypes as C
+    from rna_sequence_diff_patch_b200 import _lib
+    rng = np.random.default_rng(777)
+    lens = [(5000, 4800), (4200, 100), (6000, 6100), (300, 350), (0, 7), (4096, 4096)]
+    a = ["".join(rng.choice(list("AGCU"), size=m)) for m, _ in lens]
+    b = ["".join(rng.choice(list("AGCU"), size=n)) for _, n in lens]
+    for costs in (golden["default_costs"], golden["user_costs"]):
+        eng.set_costs(costs)
+        A, B = R.pack(a), R.pack(b)
+        routed = eng.distance_batch(A, B)
+        monkeypatch.setenv("RSD_DIST_NO_LONG", "1")
+        plain = eng.distance_batch(A, B)
+        monkeypatch.delenv("RSD_DIST_NO_LONG")
+        want = oracle_batch(a, b, costs)
+        assert np.array_equal(routed, want) and np.array_equal(plain, want)
+        # raw codes (1 byte per symbol) through rsd_distance_batch_codes
+        ca = np.concatenate([O.encode(x) for x in a]); cb = np.concatenate([O.encode(x) for x in b])
+        la = np.array([len(x) for x in a], np.int32); lb = np.array([len(x) for x in b], np.int32)
+        out = np.zeros(len(a)); mode = C.c_int()
+        _lib.check(R.load_library().rsd_distance_batch_codes(
+            eng.ctx, _lib.ptr(ca, C.c_uint8), _lib.ptr(la, C.c_int32), _lib.ptr(cb, C.c_uint8), _lib.ptr(lb, C.c_int32),
+            len(a), 0, 0, 2, 0xF, 0, _lib.ptr(out, C.c_double), C.byref(mode)))
+        assert np.array_equal(out, want)

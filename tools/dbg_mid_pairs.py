@@ -18,4 +18,10 @@ for L, K in ((10000, 200), (20000, 100), (5000, 400)):
     for rep in range(3):
         t0 = time.perf_counter(); res = eng.script_batch(A, B); t = time.perf_counter() - t0; dev = eng.last_kernel_ms()
     ok = all(np.array_equal(res["op"][p, :res["n_ops"][p]], out[p]["op"]) for p in range(0, K, 17))
+    for rep in range(3):
+        t0 = time.perf_counter(); d = eng.distance_batch(A, B); td = time.perf_counter() - t0; devd = eng.last_kernel_ms()
+    for rep in range(2):
+        t0 = time.perf_counter(); outd = eng.long_pairs(pairs, want_script=False); tl = time.perf_counter() - t0; devl = eng.last_kernel_ms()
+    okd = all(d[p] == outd[p]["dist"] for p in range(K))
+    print(f"distance_batch {K} x {L}: wall {td*1e3:.1f} ms, kernel {devd:.1f} ms = {cells/devd*1e-6:.0f} GCUPS (mode {eng.last_mode}); long_pairs distance only: wall {tl*1e3:.1f} ms, device {devl:.1f} ms = {cells/devl*1e-6:.0f} GCUPS; equal: {okd}", flush=True)
     print(f"script_batch {K} x {L}: wall {t*1e3:.1f} ms, device {dev:.1f} ms = {cells/dev*1e-6:.0f} GCUPS; same scripts: {ok}", flush=True)

@@ -891,12 +891,23 @@ static int distance_host(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int64_
     return RSD_OK;
 }
 
+// packed words -> one byte per symbol (word by word: no division per symbol)
+static void unpack_symbols(const uint32_t *words, int64_t word0, int32_t len, int bits, uint8_t *out) {
+    const int per = 32 / bits; const uint32_t msk = (1u << bits) - 1u;
+    int32_t j = 0;
+    for (int64_t w = word0; j + per <= len; ++w, j += per) {
+        uint32_t x = words[w];
+        for (int q = 0; q < per; ++q) { out[j + q] = (uint8_t)(x & msk); x >>= bits; }
+    }
+    if (j < len) { uint32_t x = words[word0 + j / per]; for (; j < len; ++j) { out[j] = (uint8_t)(x & msk); x >>= bits; } }
+}
+
 // Batches whose cells lie mostly in pairs of several thousand symbols: the panel-wavefront kernels (rsd_long_pairs,
 // distance only) run them at 2.7 TCUPS where one warp per pair with tape passes manages 1.0 / 0.5 / 0.25 TCUPS at
 // 5 / 10 / 20 kb (tools/dbg_mid_pairs.py).  -> 1 routed (out filled), 0 not applicable, < 0 error.
 static int distance_route_long(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, int bits, int force_mode, double *out, int *mode_out) {
     if (n_pairs > 65536 || force_mode == RSD_MODE_I16X2 || getenv("RSD_DIST_NO_LONG")) return 0;      // (a forced int16x2 mode keeps its own applicability error)
-    int64_t T = 4096;
+    int64_t T = 6144;                                  // by wall time the tape-pass kernel still wins at 4-5 kb (tools/dbg_crossover.py)
     if (const char *e = getenv("RSD_DIST_LONG_MIN")) T = std::max<int64_t>(atoll(e), 1);
     double cells_all = 0, cells_long = 0; int64_t total[2] = {0, 0};
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -907,7 +918,7 @@ static int distance_route_long(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, 
         if (std::max(m, n) >= T) cells_long += cells;
     }
     if (!(cells_long > 0.5 * cells_all)) return 0;
-    const int per = 32 / bits; const uint32_t msk = (1u << bits) - 1u;
+    const int per = 32 / bits;
     std::vector<uint8_t> codes[2];
     std::vector<const uint8_t *> ptr[2]; std::vector<int64_t> len64[2];
     for (int s = 0; s < 2; ++s) {
@@ -922,7 +933,7 @@ static int distance_route_long(rsd_ctx *c, const SideIn in[2], int64_t n_pairs, 
             const int64_t nw = ((int64_t)len + per - 1) / per;
             if (st0 < 0 || st0 + nw > in[s].nwords) return -rsd_fail(RSD_EINVAL, "rsd_distance_batch: pair %lld lies outside the word buffer", (long long)p);
             ptr[s][(size_t)p] = codes[s].data() + at;
-            for (int32_t j = 0; j < len; ++j) codes[s][(size_t)at++] = (uint8_t)((in[s].words[st0 + j / per] >> ((j % per) * bits)) & msk);
+            unpack_symbols(in[s].words, st0, len, bits, codes[s].data() + at); at += len;
             wat += nw;
         }
     }
@@ -1263,7 +1274,7 @@ static int script_common(rsd_ctx *c, const uint32_t *a_words, const int64_t *a_s
             if (std::max(a_len[p], b_len[p]) >= T) cells_long += cells;
         }
         if (cells_long > 0.5 * cells_all) {
-            const int per = 32 / bits; const uint32_t msk = (1u << bits) - 1u;
+            const int per = 32 / bits;
             std::vector<uint8_t> codes((size_t)total + 16);
             std::vector<const uint8_t *> pa((size_t)n_pairs), pb((size_t)n_pairs);
             std::vector<int64_t> lm((size_t)n_pairs), ln((size_t)n_pairs), mo((size_t)n_pairs), no64((size_t)n_pairs, 0);
@@ -1276,7 +1287,7 @@ static int script_common(rsd_ctx *c, const uint32_t *a_words, const int64_t *a_s
                     const int32_t len = side ? b_len[p] : a_len[p]; const int64_t nw = side ? b_nwords : a_nwords;
                     if (st0 < 0 || st0 + ((int64_t)len + per - 1) / per > nw) return rsd_fail(RSD_EINVAL, "rsd_script: pair %lld lies outside the word buffer", (long long)p);
                     (side ? pb : pa)[(size_t)p] = codes.data() + at;
-                    for (int32_t j = 0; j < len; ++j) codes[at++] = (uint8_t)((w[st0 + j / per] >> ((j % per) * bits)) & msk);
+                    unpack_symbols(w, st0, len, bits, codes.data() + at); at += (size_t)len;
                 }
                 lm[(size_t)p] = a_len[p]; ln[(size_t)p] = b_len[p]; mo[(size_t)p] = max_ops;
                 if ((int64_t)a_len[p] + b_len[p] > max_ops) return rsd_fail(RSD_EINVAL, "rsd_script: max_ops too small for pair %lld", (long long)p);

@@ -28,7 +28,7 @@ struct PlanView {
     int *bin_cnt;         // [COPIES][NB_MAX] privatised counters (copy = warp index & 7)
     int *bin_cursor;      // [COPIES][NB_MAX] per-copy cursors, preset to the copy's first rank inside its bin
     int *bin_group_off;   // [NB + 1] exclusive scan of groups per bin
-    int *bin_warp_off;    // [NB + 1] exclusive scan of warp tasks per bin
+    int *bin_warp_off;    // [NSC + 1] exclusive scan of warp tasks per strip class (tasks are cut from a class's whole group list)
     int2 *groups;         // [n_pairs] {pair A, pair B or -1}
     int *totals;          // {n_groups, n_tasks}
     int *work_counter;    // persistent-kernel ticket
@@ -117,9 +117,7 @@ __device__ __forceinline__ void plan_scan_block(const PlanView &pv) {      // on
             }
             if (c) {
                 const int groups = bin_twin(b, pv) ? (c + 1) >> 1 : c;
-                int P, G;
-                tape_shape(bin_nsq(b, pv), P, G);
-                v = ((unsigned long long)groups << 32) | (unsigned)((groups + G - 1) / G);
+                v = (unsigned long long)groups << 32;
             }
         }
         unsigned long long inc = v;
@@ -144,16 +142,30 @@ __device__ __forceinline__ void plan_scan_block(const PlanView &pv) {      // on
         __syncthreads();
         const unsigned long long excl = carry + s_warp[wid] + (inc - v);
         if (b < pv.NB) {
-            pv.bin_group_off[b] = (int)(excl >> 32); pv.bin_warp_off[b] = (int)(excl & 0xffffffffull);
+            pv.bin_group_off[b] = (int)(excl >> 32);
             // a twin bin with an odd count leaves its last group without a partner
             if ((c & 1) && bin_twin(b, pv)) pv.groups[(int)(excl >> 32) + (c >> 1)].y = -1;
         }
         carry += s_total;
         __syncthreads();
     }
+    // Warp tasks are cut from the group list of a whole strip class (all row bins of one ns, rows descending), G groups
+    // each, not bin by bin: a bin's last, partly filled task used to cost half a task per bin on average — a quarter of
+    // the work of a 74 k-pair chunk spread over 2000 (ns, m) bins.  The groups of a task now may differ a little in m
+    // (neighbouring bins); every lane keeps its own row count.  bin_warp_off[0 .. NSC] holds the task offsets per class.
+    if (t == 0) pv.bin_group_off[pv.NB] = (int)(carry >> 32);
+    __syncthreads();
     if (t == 0) {
-        pv.bin_group_off[pv.NB] = (int)(carry >> 32); pv.bin_warp_off[pv.NB] = (int)(carry & 0xffffffffull);
-        pv.totals[0] = (int)(carry >> 32); pv.totals[1] = (int)(carry & 0xffffffffull);
+        int tasks = 0;
+        for (int ci = 0; ci < pv.NSC; ++ci) {
+            pv.bin_warp_off[ci] = tasks;
+            const int groups = pv.bin_group_off[(ci + 1) * pv.MQ] - pv.bin_group_off[ci * pv.MQ];
+            int P, G;
+            tape_shape(pv.NSC - ci, P, G);
+            tasks += (groups + G - 1) / G;
+        }
+        pv.bin_warp_off[pv.NSC] = tasks;
+        pv.totals[0] = (int)(carry >> 32); pv.totals[1] = tasks;
         *pv.work_counter = 0;
     }
 }
@@ -215,18 +227,18 @@ struct TapeTask {
 };
 
 __device__ __forceinline__ TapeTask plan_decode(const PlanView &pv, int W) {
-    int lo = 0, hi = pv.NB;                        // largest b with bin_warp_off[b] <= W
+    int lo = 0, hi = pv.NSC;                       // largest strip class ci with bin_warp_off[ci] <= W
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (__ldg(&pv.bin_warp_off[mid]) <= W) lo = mid; else hi = mid;
     }
-    const int b = lo;
-    const int nsq = bin_nsq(b, pv);
+    const int ci = lo;
+    const int nsq = pv.NSC - ci;
     int P, G;
     tape_shape(nsq, P, G);
-    const int gbase = __ldg(&pv.bin_group_off[b]);
-    const int gcount = __ldg(&pv.bin_group_off[b + 1]) - gbase;
-    const int wl = W - __ldg(&pv.bin_warp_off[b]);
+    const int gbase = __ldg(&pv.bin_group_off[ci * pv.MQ]);
+    const int gcount = __ldg(&pv.bin_group_off[(ci + 1) * pv.MQ]) - gbase;
+    const int wl = W - __ldg(&pv.bin_warp_off[ci]);
     TapeTask t;
     t.ns = nsq > RSD_NSQ_MAX ? 0 : nsq;
     t.P = P;

@@ -139,11 +139,11 @@ def test_sharded_search_equals_single_shard(R, eng, golden):
         assert np.array_equal(mi, gi) and np.array_equal(ms, gs), world
 
 
-@pytest.mark.parametrize("nq,n_db,k", [(64, 120_000, 10), (130, 120_000, 10), (66, 1_100_000, 7)])
+@pytest.mark.parametrize("nq,n_db,k", [(64, 120_000, 10), (130, 120_000, 10), (66, 1_100_000, 7), (8, 2_200_000, 7)])
 def test_c5_shaped_query_batches_every_query_vs_oracle(R, eng, golden, nq, n_db, k):
     """BASELINE config 5 at its stated shape: a full batch of 64 queries (one QB batch, seed chunk spread over
-    gridDim.y), 130 queries (three batches, the last one partial) and a database that crosses the 2^20-record
-    chunk boundary — every query's top-k against the oracle (IR:466-477 + performance.py:12-15)."""
+    gridDim.y), 130 queries (three batches, the last one partial), a database of more than 2^20 records and one that crosses
+    the 2^21-record chunk boundary — every query's top-k against the oracle (IR:466-477 + performance.py:12-15)."""
     rng = np.random.default_rng(20260005 + nq)
     codes, off = make_db(rng, n_db)
     queries = make_queries(rng, codes, off, nq)

@@ -77,7 +77,7 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     ModeInfo mi_up{}; bool have_mi = false;
     long long maxc_all = 0;                          // largest |scaled cost| among the symbols of the call
     // one set of integer cost tables for the whole call: classified on the union of the symbols of every pair
-    uint32_t symmask = 0; int64_t max_m = 0, max_n = 0;
+    uint32_t symmask = 0;
     for (int p = 0; p < n_pairs; ++p) {
         LongPairPlan &Q = P[p];
         Q.m = m[p]; Q.n = n[p];
@@ -98,14 +98,14 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
             if (hi > 15) return rsd_fail(RSD_EINVAL, "rsd_long_pairs: code > 15");
             sm |= m0 | m1 | m2 | m3;
         }
-        symmask |= sm; max_m = std::max(max_m, Q.m); max_n = std::max(max_n, Q.n);
+        symmask |= sm;
     }
     // Rings and panel width, from measurements on 50 kb pairs (tools/dbg_long_batch.py, profiles/r02_long_batch_sweep.log):
     // a round of r pairs side by side (one ring each, 16 columns per lane) takes 7.6 / 11.3 / 11.0 / 16.5 ms for
     // r = 4 / 8 / 12 / 16, i.e. 1.9 / 1.4 / 0.92 / 1.03 ms per pair: about 1200 warps in flight (2 per SM scheduler) is
     // the sweet spot, more only adds contention.  So: r* = 1200 / (panels of a pair at 16 columns per lane) rings when
-    // the batch has pairs for at least two rounds of them, else one ring per pair (up to 16: a second round would cost
-    // more than the contention); 16 columns per lane once ~700 warps are in flight at 8, else 8 (a lone warp's step
+    // the batch has clearly more pairs than that (more than r* + r*/3), else one ring per pair (a second round would cost
+    // more than the contention); up to 128 rings, so batches of 5 - 20 kb pairs reach the same occupancy; 16 columns per lane once ~700 warps are in flight at 8, else 8 (a lone warp's step
     // hardly grows from 4 to 8 columns, so 4 never wins).
     int rings_want = 1;
     {

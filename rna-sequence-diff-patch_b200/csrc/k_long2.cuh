@@ -145,9 +145,12 @@ __device__ __forceinline__ void long2_panel(const LongJob2 &J, const int w, cons
         }
         auto run16 = [&](auto steady_tag) {
         constexpr bool STEADY = decltype(steady_tag)::value;
+        // steps unrolled together: 4 for the 8-column kernel with directions (a lone pair: 5.4 instead of 5.6 ms), 2 otherwise
+        // (4 costs the distance-only kernel 3 %, 8 runs the 16-column kernel out of registers)
+        constexpr int UNR = (LONG2_UNROLL == 2 && DIRS && C == 8) ? 4 : LONG2_UNROLL;
 #pragma unroll 1
         for (int k8 = 0; k8 < 16; k8 += 8) {
-#pragma unroll (LONG2_UNROLL)
+#pragma unroll (UNR)
         for (int kk = 0; kk < 8; ++kk) {
             const int k = k8 + kk;
             const int i0 = 2 * (t0 + k - lane);

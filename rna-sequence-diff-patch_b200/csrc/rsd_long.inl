@@ -71,6 +71,8 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
     RSD_OK_OR_RETURN(c->ensure_device());
     if (n_pairs == 0) return RSD_OK;
     const bool want_ij = want_script && (oi || oj);
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since_ms = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     int C = 4;
     std::vector<LongPairPlan> P((size_t)n_pairs);
     std::vector<int> fallback;                       // pairs for rsd_long_pair (fp64 / exact-double keys)
@@ -397,7 +399,9 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     RSD_CUDA(cudaMemcpyAsync(h_oj, d_oj, 4 * ops_entries, cudaMemcpyDeviceToHost, st));
                 }
             }
+            const double t_enq = since_ms(t_entry);
             RSD_CUDA(cudaStreamSynchronize(st));
+            const double t_sync = since_ms(t_entry);
             if (c->timing) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev_t1[0]) == cudaSuccess) fwd_ms_total = ms; }
             {
                 size_t oo = 0;
@@ -415,8 +419,8 @@ extern "C" int rsd_long_pairs(rsd_ctx *c, int n_pairs, const uint8_t *const *a, 
                     }
                 }
             }
-            if (ltrace) fprintf(stderr, "[rsd trace] long batch: %zu pair(s)%s, %zu launch(es), %zu MB, blocks %d x ranges %d of pair %d\n", batch.size(), solo ? " (blocked)" : "",
-                                launches.size(), need >> 20, P[batch[0]].nb, P[batch[0]].nr, batch[0]);
+            if (ltrace) fprintf(stderr, "[rsd trace] long batch: %zu pair(s)%s, %zu launch(es), %zu MB, blocks %d x ranges %d of pair %d; host ms since entry: enqueued %.2f, device done %.2f, results out %.2f\n",
+                                batch.size(), solo ? " (blocked)" : "", launches.size(), need >> 20, P[batch[0]].nb, P[batch[0]].nr, batch[0], t_enq, t_sync, since_ms(t_entry));
             first_batch = false;
         }
         c->long_fwd_ms = fwd_ms_total;

@@ -234,7 +234,7 @@ class Engine:
         a = np.ascontiguousarray(a_codes, np.uint8) if m else np.zeros(1, np.uint8)
         b = np.ascontiguousarray(b_codes, np.uint8) if n else np.zeros(1, np.uint8)
         max_ops = m + n + 1 if want_script else 1
-        op = np.zeros(max_ops, np.uint8); oi = np.zeros(max_ops, np.int32); oj = np.zeros(max_ops, np.int32)
+        op = np.empty(max_ops, np.uint8); oi = np.empty(max_ops, np.int32); oj = np.empty(max_ops, np.int32)     # only [:n_ops] is handed out
         n_ops = C.c_int64(); dist = C.c_double(); mode = C.c_int()
         check(self._lib.rsd_long_pair(self._ctx, ptr(a, _u8), m, ptr(b, _u8), n, force_mode, int(want_script), max_ops,
                                       ptr(op, _u8), ptr(oi, _i32), ptr(oj, _i32), C.byref(n_ops), C.byref(dist),
@@ -253,8 +253,9 @@ class Engine:
         B = [np.ascontiguousarray(b, np.uint8) if b.shape[0] else np.zeros(1, np.uint8) for _, b in pairs]
         m = np.array([a.shape[0] for a, _ in pairs], np.int64); n = np.array([b.shape[0] for _, b in pairs], np.int64)
         max_ops = (m + n + 1) if want_script else np.ones(K, np.int64)
-        op = [np.zeros(int(k), np.uint8) for k in max_ops]
-        oi = [np.zeros(int(k), np.int32) for k in max_ops]; oj = [np.zeros(int(k), np.int32) for k in max_ops]
+        # np.empty: only [:n_ops] is handed out, and calloc of 72 recycled 100 - 400 KB chunks costs several ms per call
+        op = [np.empty(int(k), np.uint8) for k in max_ops]
+        oi = [np.empty(int(k), np.int32) for k in max_ops]; oj = [np.empty(int(k), np.int32) for k in max_ops]
         parr = lambda xs: (C.c_void_p * K)(*[x.ctypes.data for x in xs])
         n_ops = np.zeros(K, np.int64); dist = np.zeros(K, np.float64); mode = (C.c_int * K)()
         check(self._lib.rsd_long_pairs(self._ctx, K, parr(A), ptr(m, _i64), parr(B), ptr(n, _i64), force_mode, int(want_script),
